@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI declared in include/dincae_b200.h.
+
+The shared library is built in-tree by ``python -m dincae_b200.build`` (nvcc, sm_100a).
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_uint16, c_uint64, c_uint8, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdincae_b200.so")
+
+_lib = None
+
+vp = c_void_p
+
+# name -> (restype, argtypes); mirrors include/dincae_b200.h one to one
+SIGNATURES = {
+    "dincae_version": (c_char_p, []),
+    "dincae_error_string": (c_char_p, [c_int]),
+    "dincae_last_cuda_error": (c_int, []),
+    "dincae_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "dincae_prepare_cube": (c_int, [vp, vp, c_int, c_int, c_int, c_double, c_int, vp, vp, vp, vp]),
+    "dincae_build_batch": (c_int, [vp, vp, vp, vp, vp, vp, vp, POINTER(c_double), POINTER(c_double),
+                                   c_int, c_int, c_int, c_int, c_int, vp, vp, c_int, vp, c_uint64,
+                                   vp, vp, c_int, vp, vp, vp]),
+    "dincae_conv3x3_fwd": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int,
+                                   c_int, c_float, vp, vp, vp, vp]),
+    "dincae_conv3x3_dgrad": (c_int, [vp, vp, vp, c_float, c_int, vp, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, vp, c_float, vp, c_int, vp, vp, vp]),
+    "dincae_conv3x3_wgrad_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "dincae_conv3x3_wgrad": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
+                                     c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]),
+    "dincae_dense_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "dincae_dense_fwd": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
+    "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
+    "dincae_dense_bwd_weight": (c_int, [vp, vp, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_head_recon": (c_int, [vp, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_head_loss_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "dincae_head_loss": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_float, vp, vp, vp, vp, vp,
+                                 c_size_t, vp]),
+    "dincae_adam_workspace": (c_size_t, [c_size_t]),
+    "dincae_adam_step": (c_int, [vp, vp, vp, vp, c_size_t, c_size_t, c_float, c_float, vp, c_float,
+                                 c_float, c_float, c_float, vp, vp, vp, c_size_t, vp]),
+    "dincae_l2_half_sumsq": (c_int, [vp, c_size_t, vp, vp, c_size_t, vp]),
+}
+
+
+class DincaeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DincaeError(
+            "%s not found: build the CUDA extension first (python -m dincae_b200.build). "
+            "dincae_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        lib = load()
+        msg = lib.dincae_error_string(rc).decode()
+        raise DincaeError("%s failed: %s (code %d, cuda error %d)" %
+                          (what or "dincae call", msg, rc, lib.dincae_last_cuda_error()))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def doubles(values):
+    arr = (c_double * len(values))(*[float(v) for v in values])
+    return arr

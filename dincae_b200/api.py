@@ -1,0 +1,400 @@
+"""Drop-in replacement of the reference's public functions (DINCAE/__init__.py:47-51,
+:53-117, :120-230, :234-294, :302-329, :704-811): same names, same positional and keyword
+arguments, same netCDF output layout -- executed by the sm_100a kernels of this package.
+"""
+import os
+import random
+from datetime import datetime, timedelta
+from math import ceil
+
+import numpy as np
+
+from . import ncio
+
+__all__ = ["reconstruct", "load_gridded_nc", "data_generator", "reconstruct_gridded_nc"]
+
+NEAREST_NEIGHBOR = 1        # tf.image.ResizeMethod.NEAREST_NEIGHBOR in TF 1.15
+
+
+def identity(x):
+    return x
+
+
+def sinv(x, minx=1e-3):
+    """"Safe inversion" of DINCAE/__init__.py:298-299 for numpy / torch inputs."""
+    try:
+        import torch
+        if isinstance(x, torch.Tensor):
+            return 1 / torch.clamp(x, min=minx)
+    except ImportError:                 # pragma: no cover
+        pass
+    return 1 / np.maximum(x, minx)
+
+
+def load_gridded_nc(fname, varname, minfrac=0.05):
+    """Same contract as the reference (:53-117): returns
+    ``lon, lat, time, data (masked), missing (bool), mask (bool)``."""
+    lon, lat, time, data, mask = ncio.read_gridded(fname, varname)
+    data = np.ma.asarray(data)
+    if mask is not None:
+        mask = np.asarray(mask) == 1
+    else:
+        print("compute mask for ", varname, ": sea point should have at least ",
+              minfrac, " for valid data tought time")
+        if data.mask is np.ma.nomask or np.isscalar(data.mask):
+            mask = np.ones((data.shape[1], data.shape[2]), dtype=bool)
+        else:
+            mask = np.mean(~data.mask, axis=0) > minfrac
+        print("mask: sea points ", np.sum(mask))
+        print("mask: land points ", np.sum(~mask))
+    print("varname ", varname, mask.shape)
+    if data.mask is np.ma.nomask or np.isscalar(data.mask):
+        missing = np.zeros(data.shape, dtype=bool)
+    else:
+        missing = data.mask
+    print("data shape: ", data.shape)
+    print("data range: ", data.min(), data.max())
+    return lon, lat, time, data, missing, mask
+
+
+_recent_sources = []
+
+
+class FrameSource:
+    """Callable with the reference's generator protocol (``datagen()`` yields
+    ``(xin[H,W,nvar] f32, xtrue[H,W,2] f32)`` frame by frame, :196-227) that also carries
+    its source arrays, so ``reconstruct`` can keep the cube in HBM and build batches on the
+    GPU instead of pulling frames through Python."""
+
+    def __init__(self, lon, lat, time, data_full, missing, train, ntime_win, obs_err_std,
+                 jitter_std):
+        self.lon, self.lat, self.time = lon, lat, time
+        self.data_full, self.missing = list(data_full), list(missing)
+        self.train = bool(train)
+        self.ntime_win = int(ntime_win)
+        self.obs_err_std = list(obs_err_std)
+        self.jitter_std = list(jitter_std)
+        self._cube = None
+
+    def same_data(self, other):
+        return (isinstance(other, FrameSource) and len(other.data_full) == len(self.data_full)
+                and all(a is b for a, b in zip(self.data_full, other.data_full))
+                and all(a is b for a, b in zip(self.missing, other.missing))
+                and self.ntime_win == other.ntime_win and self.obs_err_std == other.obs_err_std)
+
+    def cube(self):
+        """Device cube of this source; sources built from the same arrays share one."""
+        from .data import DeviceCube
+        if self._cube is None:
+            for other in _recent_sources:
+                if other._cube is not None and self.same_data(other):
+                    self._cube = other._cube
+                    break
+            else:
+                self._cube = DeviceCube(self.lon, self.lat, self.time, self.data_full, self.missing,
+                                        self.obs_err_std, self.ntime_win)
+            _recent_sources.append(self)
+            del _recent_sources[:-4]
+        return self._cube
+
+    @property
+    def ntime(self):
+        return self.data_full[0].shape[0]
+
+    def __call__(self, chunk=16):
+        """Frames in time order, produced by the GPU batch builder and copied back."""
+        import torch
+        from . import layout
+        cube = self.cube()
+        T, H, W = cube.T, cube.H, cube.W
+        xin = torch.zeros(chunk, cube.nvar_planes, H, W, 4, device=cube.dev)
+        xtrue = torch.zeros(chunk, H, W, 2, device=cube.dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=cube.dev)
+        seed = random.getrandbits(63) if self.train else 0
+        for start in range(0, T, chunk):
+            n = min(chunk, T - start)
+            fi = torch.arange(start, start + n, dtype=torch.int32, device=cube.dev)
+            ci = None
+            if self.train:
+                ci = torch.tensor([random.randrange(0, T) for _ in range(n)], dtype=torch.int32,
+                                  device=cube.dev)
+            cube.build_batch(fi, ci, n, xin, xtrue, cnt, jitter_std=self.jitter_std, seed=seed)
+            a = layout.p4_to_nhwc(xin[:n].cpu().numpy(), cube.nvar)
+            t = xtrue[:n].cpu().numpy()
+            for k in range(n):
+                yield a[k], t[k]
+
+
+def data_generator_list(lon, lat, time, data_full, missing, train=True, ntime_win=3,
+                        obs_err_std=[1.], jitter_std=[0.05]):
+    """(:132-230) -> ``datagen, nvar, ntime, meandata``; ``meandata`` of the first variable."""
+    sz = data_full[0].shape
+    print("sz ", sz)
+    src = FrameSource(lon, lat, time, data_full, missing, train, ntime_win, obs_err_std, jitter_std)
+    cube = src.cube()
+    return src, cube.nvar, cube.T, cube.meandata[0]
+
+
+def data_generator(lon, lat, time, data_full, missing, train=True, ntime_win=3, obs_err_std=1.,
+                   jitter_std=0.05):
+    """(:120-130).  Like the reference, the ``train`` argument is NOT forwarded (the list
+    version is always called with train=True; quirk Q1 of SURVEY.md)."""
+    return data_generator_list(lon, lat, time, [data_full], [missing], train=True,
+                               ntime_win=ntime_win, obs_err_std=[obs_err_std],
+                               jitter_std=[jitter_std])
+
+
+def savesample(fname, m_rec, σ2_rec, meandata, lon, lat, e, ii, offset,
+               transfun=(identity, identity)):
+    """(:234-294) write one batch of the reconstruction; creates the file at ``ii == 0``."""
+    recdata = transfun[1](m_rec + meandata)
+    if transfun[1] not in (np.exp, identity):
+        print("warning: sigma_rec is not transformed")
+    sigma_rec = np.sqrt(σ2_rec)
+    w = _open_writers.get(fname)
+    if ii == 0 or w is None:
+        if w is not None:
+            w.close()
+        w = ncio.ReconWriter(fname, lon, lat, meandata, append=(ii != 0 and os.path.isfile(fname)))
+        _open_writers[fname] = w
+    w.write(offset, np.asarray(recdata), np.asarray(sigma_rec))
+
+
+_open_writers = {}
+
+
+def _close_writer(fname):
+    w = _open_writers.pop(fname, None)
+    if w is not None:
+        w.close()
+
+
+_last_stamp = [None]
+
+
+def _output_name(outdir):
+    """``data-%Y-%m-%dT%H%M%S.nc`` (:674-675); bumped by whole seconds when two saves fall
+    into the same second (a B200 epoch is shorter than the 1 s resolution of the name)."""
+    now = datetime.now().replace(microsecond=0)
+    if _last_stamp[0] is not None and now <= _last_stamp[0]:
+        now = _last_stamp[0] + timedelta(seconds=1)
+    _last_stamp[0] = now
+    return os.path.join(outdir, "data-{}.nc".format(now.strftime("%Y-%m-%dT%H%M%S")))
+
+
+def reconstruct(lon, lat, mask, meandata,
+                train_datagen, train_len,
+                test_datagen, test_len,
+                outdir,
+                resize_method=NEAREST_NEIGHBOR,
+                epochs=1000,
+                batch_size=30,
+                save_each=10,
+                save_model_each=500,
+                skipconnections=[1, 2, 3, 4],
+                dropout_rate_train=0.3,
+                tensorboard=False,
+                truth_uncertain=False,
+                shuffle_buffer_size=3 * 15,
+                nvar=10,
+                enc_nfilter_internal=[16, 24, 36, 54],
+                frac_dense_layer=[0.2],
+                clip_grad=5.0,
+                regularization_L2_beta=0,
+                transfun=(identity, identity),
+                savesample=savesample,
+                learning_rate=1e-3,
+                learning_rate_decay_epoch=np.inf,
+                iseed=None,
+                nprefetch=0,
+                loss=[],
+                nepoch_keep_missing=0,
+                ):
+    """Train the network and periodically reconstruct the test set; returns the filename
+    of the latest reconstruction.  Arguments as in the reference (:302-369).
+
+    Differences that do not change results: ``dropout_rate_train`` and ``nprefetch`` are
+    accepted and ignored (dropout never fires in the reference; the feed is
+    on the GPU); only nearest-neighbour ``resize_method`` exists; ``tensorboard`` writes
+    scalars only when ``torch.utils.tensorboard`` is importable.
+    """
+    import torch
+    from .engine import Plan
+    from .sampler import TrainSampler, sequential_batches
+    from .trainer import Reconstructor, Trainer
+
+    if resize_method not in (NEAREST_NEIGHBOR, "nearest", None):
+        raise ValueError("dincae_b200 implements only nearest-neighbour upsampling "
+                         "(resize_method=tf.image.ResizeMethod.NEAREST_NEIGHBOR == 1)")
+    init_seed, shuffle_seed, noise_seed = 0, None, random.getrandbits(62)
+    if iseed is not None:
+        # same draw order as :372-375 (np.random -> TF graph seed -> python random)
+        np.random.seed(iseed)
+        init_seed = int(np.random.randint(0, 2 ** 32 - 1))
+        random.seed(int(np.random.randint(0, 2 ** 32 - 1)))
+        shuffle_seed = init_seed
+        noise_seed = init_seed
+
+    print("regularization_L2_beta ", regularization_L2_beta)
+    print("enc_nfilter_internal ", enc_nfilter_internal)
+    print("nvar ", nvar)
+    print("nepoch_keep_missing ", nepoch_keep_missing)
+
+    if outdir is not None and not os.path.isdir(outdir):
+        os.mkdir(outdir)
+
+    jmax, imax = mask.shape
+    plan = Plan(jmax, imax, nvar, enc_nfilter_internal, frac_dense_layer, skipconnections)
+
+    if not isinstance(train_datagen, FrameSource) or not isinstance(test_datagen, FrameSource):
+        from .hostfeed import reconstruct_from_generators
+        return reconstruct_from_generators(
+            plan, lon, lat, mask, meandata, train_datagen, train_len, test_datagen, test_len,
+            outdir, epochs=epochs, batch_size=batch_size, save_each=save_each,
+            truth_uncertain=truth_uncertain, shuffle_buffer_size=shuffle_buffer_size,
+            clip_grad=clip_grad, regularization_L2_beta=regularization_L2_beta, transfun=transfun,
+            savesample=savesample, learning_rate=learning_rate,
+            learning_rate_decay_epoch=learning_rate_decay_epoch, init_seed=init_seed,
+            shuffle_seed=shuffle_seed, loss=loss, output_name=_output_name,
+            close_writer=_close_writer)
+
+    cube = train_datagen.cube()
+    test_cube = test_datagen.cube()
+    if cube.nvar != nvar:
+        raise ValueError("nvar=%d does not match the generator (%d)" % (nvar, cube.nvar))
+
+    trainer = Trainer(plan, cube, batch_size, truth_uncertain=truth_uncertain,
+                      clip_grad=clip_grad, l2_beta=regularization_L2_beta,
+                      noise_seed=noise_seed, init_seed=init_seed,
+                      jitter_std=train_datagen.jitter_std)
+    sampler = TrainSampler(train_len, batch_size, shuffle_buffer_size, seed=shuffle_seed,
+                           train=train_datagen.train)
+    recon = Reconstructor(plan, test_cube, batch_size, net=trainer.net,
+                          train_mode_inputs=test_datagen.train, noise_seed=noise_seed + 1,
+                          jitter_std=test_datagen.jitter_std)
+    writer_tb = None
+    if tensorboard and outdir is not None:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer_tb = SummaryWriter(os.path.join(outdir, "train"))
+        except Exception:            # noqa: BLE001
+            writer_tb = None
+
+    dt_start = datetime.now()
+    print(dt_start)
+    fname = None
+    index = 0
+    steps_per_epoch = ceil(train_len / batch_size)
+
+    def drain(e, first_step):
+        nonlocal index
+        for k, (c, r) in enumerate(trainer.flush_losses()):
+            loss.append(c)
+            if writer_tb is not None:
+                writer_tb.add_scalar("Validation/cost", c, index)
+                writer_tb.add_scalar("Validation/RMS", r, index)
+            index += 1
+            ii = first_step + k
+            if ii % 20 == 0:
+                print("Epoch: {}/{}...".format(e + 1, epochs),
+                      "Training loss: {:.20f}".format(c), "RMS: {:.20f}".format(r), lr_e)
+
+    for e in range(epochs):
+        if nepoch_keep_missing > 0:
+            random.seed(iseed + e // nepoch_keep_missing)        # :639-641
+        lr_e = learning_rate * (0.5 ** (e / learning_rate_decay_epoch))
+        trainer.set_lr(lr_e)
+        for ii in range(steps_per_epoch):
+            fi, ci, seq = sampler.next_batch()
+            trainer.train_step(fi, ci, seq)
+        drain(e, 0)
+
+        if ((e == epochs - 1) or ((save_each > 0) and (e % save_each == 0))) and outdir is not None:
+            print("Save output", e)
+            fname = _output_name(outdir)
+            pending = None
+            for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
+                out = recon.run_batch(frames, slot=ii % 2)
+                if pending is not None:
+                    _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending = (out, len(frames), ii, ii * batch_size, ev)
+            if pending is not None:
+                _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
+            _close_writer(fname)
+
+        if (save_model_each > 0) and (e % save_model_each == 0) and outdir is not None:
+            save_checkpoint(os.path.join(outdir, "model-{:03d}.ckpt".format(e + 1)), trainer)
+
+    if writer_tb is not None:
+        writer_tb.close()
+    dt_end = datetime.now()
+    print(dt_end)
+    print(dt_end - dt_start)
+    return fname
+
+
+def _emit(savesample_fn, fname, pending, meandata, lon, lat, e, transfun):
+    out, n, ii, offset, ev = pending
+    ev.synchronize()
+    arr = out.numpy()
+    savesample_fn(fname, arr[0, :n], arr[1, :n], meandata, lon, lat, e, ii, offset,
+                  transfun=transfun)
+
+
+def save_checkpoint(path, trainer):
+    """Counterpart of ``saver.save`` (:691-693): the 20 variables in TF order/shape plus the
+    Adam slots, as a torch file ``<path>.pt`` (the reference has no restore path)."""
+    import torch
+    net = trainer.net
+    torch.save({
+        "names": [e["name"] for e in net.plan.entries],
+        "params": net.get_params_tf(),
+        "adam_m": net.plan.unpack(net.adam_m.cpu().numpy()),
+        "adam_v": net.plan.unpack(net.adam_v.cpu().numpy()),
+        "adam_state": net.adam_state.cpu().numpy(),
+        "step": trainer.step_count,
+    }, path + ".pt")
+    return path + ".pt"
+
+
+def reconstruct_gridded_nc(filename, varname, outdir, jitter_std=0.05, ntime_win=3,
+                           transfun=(identity, identity), **kwargs):
+    """(:704-740).  Bug-compatible with the reference: ``transfun[0]`` is not applied to the
+    input (Q5), the "test" generator is built in train mode (Q1), and ``None`` is returned
+    (Q7)."""
+    lon, lat, time, data, missing, mask = load_gridded_nc(filename, varname)
+    train_datagen, nvar, train_len, meandata = data_generator(
+        lon, lat, time, data, missing, ntime_win=ntime_win, jitter_std=jitter_std)
+    test_datagen, nvar, test_len, test_meandata = data_generator(
+        lon, lat, time, data, missing, ntime_win=ntime_win, train=False)
+    print("Number of input variables: ", nvar)
+    reconstruct(lon, lat, mask, meandata, train_datagen, train_len, test_datagen, test_len,
+                outdir, transfun=transfun, nvar=nvar, **kwargs)
+
+
+def reconstruct_gridded_files(fields, outdir, ntime_win=3, **kwargs):
+    """(:744-811) multivariate driver; reconstructs the first field, returns the filename."""
+    n = len(fields)
+    data_full, missing = [None] * n, [None] * n
+    jitter_std, transfun = [None] * n, [None] * n
+    obs_err_std = [1] * n
+    for i, field in enumerate(fields):
+        transfun[i] = field.get("transfun", (identity, identity))
+        (field["lon"], field["lat"], field["time"], field["data"], field["missing"],
+         field["mask"]) = load_gridded_nc(field["filename"], field["varname"])
+        data_full[i] = transfun[i][0](field["data"])
+        missing[i] = field["missing"]
+        jitter_std[i] = field.get("jitter_std", 0)
+    lon, lat = fields[0]["lon"], fields[0]["lat"]
+    time, mask = fields[0]["time"], fields[0]["mask"]
+    train_datagen, nvar, train_len, meandata = data_generator_list(
+        lon, lat, time, data_full, missing, obs_err_std=obs_err_std, jitter_std=jitter_std,
+        ntime_win=ntime_win)
+    test_datagen, nvar, test_len, test_meandata = data_generator_list(
+        lon, lat, time, data_full, missing, obs_err_std=obs_err_std, ntime_win=ntime_win,
+        train=False)
+    print("Number of input variables: ", nvar)
+    return reconstruct(lon, lat, mask, meandata, train_datagen, train_len, test_datagen,
+                       test_len, outdir, transfun=transfun[0], nvar=nvar, **kwargs)

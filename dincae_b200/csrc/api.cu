@@ -1,0 +1,34 @@
+// Library-level entry points of the C ABI (version, errors, device query).
+#include "common.cuh"
+
+namespace dincae {
+int g_last_cuda_error = 0;
+}
+
+extern "C" const char* dincae_version(void) { return "dincae_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char* dincae_error_string(int code) {
+  switch (code) {
+    case DINCAE_OK: return "ok";
+    case DINCAE_EINVAL: return "invalid argument";
+    case DINCAE_ECUDA: return "CUDA error";
+    case DINCAE_ENOSPC: return "workspace too small";
+    case DINCAE_EARCH: return "device is not sm_100";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int dincae_last_cuda_error(void) { return dincae::g_last_cuda_error; }
+
+extern "C" int dincae_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return dincae::cuda_rc(e);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return dincae::cuda_rc(e);
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return DINCAE_OK;
+}

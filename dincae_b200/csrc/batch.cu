@@ -1,0 +1,251 @@
+// Input pipeline on the device: temporal-mean removal and the per-batch channel stacking,
+// added-cloud masking and jitter of DINCAE/__init__.py:155-227.  HBM-bound gather kernels.
+#include "common.cuh"
+
+namespace dincae {
+
+// ---------------------------------------------------------------------------------------
+// prepare_cube: one thread per pixel walks the time axis twice (coalesced across pixels).
+// numpy's MaskedArray.mean over axis 0 adds the 0-filled float32 slices in time order,
+// then divides in float64; the anomaly and the division by obs_var are float64 too and are
+// rounded to float32 once when stored (DINCAE/__init__.py:168-169,180).
+// ---------------------------------------------------------------------------------------
+__global__ void prepare_cube_kernel(const float* __restrict__ data,
+                                    const uint8_t* __restrict__ missing, int T, size_t HW,
+                                    double obs_var, int nomask, float* __restrict__ anom,
+                                    double* __restrict__ meandata, uint8_t* __restrict__ never) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float sum = 0.f;
+  int count = 0;
+  for (int t = 0; t < T; ++t) {
+    const bool miss = missing[(size_t)t * HW + p] != 0;
+    const float v = miss ? 0.f : data[(size_t)t * HW + p];
+    sum = __fadd_rn(sum, v);
+    count += miss ? 0 : 1;
+  }
+  double mean;
+  if (nomask) {
+    mean = (double)__fdiv_rn(sum, (float)T);          // ndarray.mean of float32 stays float32
+  } else {
+    mean = count > 0 ? __ddiv_rn((double)sum * 1.0, (double)count) : 0.0;
+  }
+  meandata[p] = mean;
+  never[p] = (count == 0) ? 1 : 0;
+  for (int t = 0; t < T; ++t) {
+    const bool miss = missing[(size_t)t * HW + p] != 0;
+    float a = 0.f;
+    if (!miss && count > 0) {
+      const double d = __dsub_rn((double)data[(size_t)t * HW + p], mean);
+      a = (float)__ddiv_rn(d, obs_var);
+    }
+    anom[(size_t)t * HW + p] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) + Box-Muller: counter-based normals so that the noise
+// of a frame depends only on (seed, sequence number of the frame, pixel, slot) and not on
+// batch composition or GPU count.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
+  const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+#define DINCAE_MAX_NDATA 8
+
+struct BatchParams {
+  const float* anom;
+  const uint8_t* missing;
+  const uint8_t* cloud_missing;
+  const float* lon_scaled;
+  const float* lat_scaled;
+  const float* doy_cos;
+  const float* doy_sin;
+  const int32_t* frame_idx;
+  const int32_t* cloud_idx;
+  const double* noise;
+  const int64_t* noise_seq;
+  float* xin;
+  float* xtrue;
+  int32_t* n_noncloud;
+  uint64_t seed;
+  int ndata, T, H, W, ntime_win, B, nvar_planes;
+  float inv_var[DINCAE_MAX_NDATA];
+  double jitter[DINCAE_MAX_NDATA];
+};
+
+// One thread per (b, y, x).  All nvar channels of the pixel are produced plane by plane
+// (float4 stores, coalesced along x).
+__global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
+  const int HW = P.H * P.W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = gid < (long long)P.B * HW;
+  int cnt = 0;
+  if (active) {
+    const int b = (int)(gid / HW);
+    const int p = (int)(gid - (long long)b * HW);
+    const int y = p / P.W, x = p - y * P.W;
+    const int i = P.frame_idx[b];
+    const int nd = P.ndata, nd2 = 2 * nd;
+    const size_t THW = (size_t)P.T * HW;
+    const bool train = P.cloud_idx != nullptr;
+    const int ic = train ? P.cloud_idx[b] : 0;
+    const int nvar = nd2 * P.ntime_win + 4;
+    const int half = P.ntime_win / 2;
+
+    // jitter slots per variable j: channels 2j, 2j+2nd+4, 2j+4nd+4 (reference quirk Q4)
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    float gauss[4] = {0.f, 0.f, 0.f, 0.f};
+    int gauss_j = -1;
+
+    float lane[4];
+    for (int plane = 0; plane < P.nvar_planes; ++plane) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = plane * 4 + k;
+        float v = 0.f;
+        if (c < nvar) {
+          int j = -1, kind = 0, slot = -1, frame = i;
+          if (c < nd2) {
+            j = c >> 1; kind = c & 1; slot = 0;
+          } else if (c < nd2 + 4) {
+            const int s = c - nd2;
+            v = s == 0 ? P.lon_scaled[x] : (s == 1 ? P.lat_scaled[y]
+                                                   : (s == 2 ? P.doy_cos[i] : P.doy_sin[i]));
+          } else {
+            const int r = c - nd2 - 4;
+            const int w = r / nd2;                 // neighbour slot 0 .. ntime_win-2
+            const int rr = r - w * nd2;
+            j = rr >> 1; kind = rr & 1; slot = w + 1;
+            int nn = w - half;                     // offsets in order, centre skipped
+            if (nn >= 0) nn += 1;
+            frame = min(P.T - 1, max(0, i + nn));
+          }
+          if (j >= 0) {
+            const size_t at = (size_t)j * THW + (size_t)frame * HW + p;
+            const bool miss = P.missing[at] != 0;
+            bool clouded = false;
+            if (train && slot == 0)
+              clouded = P.cloud_missing[(size_t)j * THW + (size_t)ic * HW + p] != 0;
+            if (kind == 0) {
+              v = (miss || clouded) ? 0.f : P.anom[at];
+              if (train && slot <= 2) {
+                if (P.noise != nullptr) {
+                  const double z = P.noise[((size_t)b * 3 * nd + 3 * j + slot) * HW + p];
+                  v = (float)((double)v + P.jitter[j] * z);
+                } else if (P.jitter[j] != 0.0) {
+                  if (gauss_j != j) {
+                    const uint64_t seq = P.noise_seq ? (uint64_t)P.noise_seq[b] : (uint64_t)i;
+                    rnd = philox4x32_10(
+                        make_uint4((uint32_t)p, (uint32_t)j, (uint32_t)seq, (uint32_t)(seq >> 32)),
+                        make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                    const float2 g0 = box_muller(rnd.x, rnd.y);
+                    const float2 g1 = box_muller(rnd.z, rnd.w);
+                    gauss[0] = g0.x; gauss[1] = g0.y; gauss[2] = g1.x; gauss[3] = g1.y;
+                    gauss_j = j;
+                  }
+                  v = fmaf((float)P.jitter[j], gauss[slot], v);
+                }
+              }
+            } else {
+              v = (miss || clouded) ? 0.f : P.inv_var[j];
+            }
+          }
+        }
+        lane[k] = v;
+      }
+      reinterpret_cast<float4*>(P.xin)[((size_t)(b * P.nvar_planes + plane) * P.H + y) * P.W + x] =
+          make_float4(lane[0], lane[1], lane[2], lane[3]);
+    }
+    // target: un-perturbed channels 0 and 1 of the current frame (:227)
+    {
+      const size_t at = (size_t)i * HW + p;
+      const bool miss = P.missing[at] != 0;
+      const float t0 = miss ? 0.f : P.anom[at];
+      const float t1 = miss ? 0.f : P.inv_var[0];
+      reinterpret_cast<float2*>(P.xtrue)[(size_t)b * HW + p] = make_float2(t0, t1);
+      cnt = (t1 != 0.f) ? 1 : 0;
+    }
+  }
+  // count of observed target pixels: integer, hence order-independent
+  unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
+  __shared__ int block_cnt;
+  if (threadIdx.x == 0) block_cnt = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&block_cnt, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0 && block_cnt) atomicAdd(P.n_noncloud, block_cnt);
+}
+
+}  // namespace dincae
+
+using namespace dincae;
+
+extern "C" int dincae_prepare_cube(const float* data, const uint8_t* missing, int T, int H, int W,
+                                   double obs_var, int nomask, float* anom, double* meandata,
+                                   uint8_t* never, void* stream) {
+  if (!data || !missing || !anom || !meandata || !never || T <= 0 || H <= 0 || W <= 0)
+    return DINCAE_EINVAL;
+  const size_t HW = (size_t)H * W;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((HW + threads - 1) / threads);
+  prepare_cube_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      data, missing, T, HW, obs_var, nomask, anom, meandata, never);
+  return check_launch();
+}
+
+extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
+                                  const uint8_t* cloud_missing,
+                                  const float* lon_scaled, const float* lat_scaled,
+                                  const float* doy_cos, const float* doy_sin,
+                                  const double* inv_var_host, const double* jitter_std_host,
+                                  int ndata, int T, int H, int W, int ntime_win,
+                                  const int32_t* frame_idx, const int32_t* cloud_idx, int B,
+                                  const double* noise, uint64_t seed, const int64_t* noise_seq,
+                                  float* xin, int nvar_planes, float* xtrue,
+                                  int32_t* n_noncloud, void* stream) {
+  if (!anom || !missing || !lon_scaled || !lat_scaled || !doy_cos || !doy_sin || !inv_var_host ||
+      !frame_idx || !xin || !xtrue || !n_noncloud)
+    return DINCAE_EINVAL;
+  if (ndata <= 0 || ndata > DINCAE_MAX_NDATA || T <= 0 || H <= 0 || W <= 0 || B <= 0 ||
+      ntime_win < 1 || (ntime_win & 1) == 0)
+    return DINCAE_EINVAL;
+  const int nvar = 2 * ndata * ntime_win + 4;
+  if (nvar_planes * 4 < nvar) return DINCAE_EINVAL;
+  if (cloud_idx && ntime_win < 3) return DINCAE_EINVAL;   // reference raises IndexError (Q4)
+  BatchParams P;
+  P.anom = anom; P.missing = missing; P.cloud_missing = cloud_missing ? cloud_missing : missing; P.lon_scaled = lon_scaled; P.lat_scaled = lat_scaled;
+  P.doy_cos = doy_cos; P.doy_sin = doy_sin; P.frame_idx = frame_idx; P.cloud_idx = cloud_idx;
+  P.noise = noise; P.noise_seq = noise_seq; P.xin = xin; P.xtrue = xtrue;
+  P.n_noncloud = n_noncloud; P.seed = seed;
+  P.ndata = ndata; P.T = T; P.H = H; P.W = W; P.ntime_win = ntime_win; P.B = B;
+  P.nvar_planes = nvar_planes;
+  for (int j = 0; j < DINCAE_MAX_NDATA; ++j) {
+    P.inv_var[j] = j < ndata ? (float)inv_var_host[j] : 0.f;
+    P.jitter[j] = (j < ndata && jitter_std_host) ? jitter_std_host[j] : 0.0;
+  }
+  const long long total = (long long)B * H * W;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  build_batch_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(P);
+  return check_launch();
+}

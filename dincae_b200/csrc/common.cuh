@@ -1,0 +1,100 @@
+// Shared helpers for the dincae_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dincae_b200.h"
+
+namespace dincae {
+
+extern int g_last_cuda_error;
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return DINCAE_ECUDA;
+  }
+  return DINCAE_OK;
+}
+
+inline int cuda_rc(cudaError_t e) {
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return DINCAE_ECUDA;
+  }
+  return DINCAE_OK;
+}
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) {
+  return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+__device__ __forceinline__ float f4_dot(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+__device__ __forceinline__ float f4_get(const float4& a, int i) {
+  return i == 0 ? a.x : (i == 1 ? a.y : (i == 2 ? a.z : a.w));
+}
+
+// Logical conv input U[b][plane][y][x] (one float4 = 4 channels) assembled on the fly:
+//   mode 0: concat(s0 [p0 planes, optionally stored at half resolution], s1 [p1 planes])
+//   mode 1: gradient of an encoder stage: gpool[y>>1][x>>1] / window_count * lrelu'(sign)
+struct ConvSrc {
+  const float4* s0;
+  const float4* s1;
+  const uint16_t* sign;
+  int p0, p1;
+  int half0;
+  int mode;
+  float slope;
+  int H, W, Hh, Wh, Wq;   // full size, half size, ceil(W/4)
+  __host__ __device__ __forceinline__ int planes() const { return p0 + p1; }
+};
+
+__device__ __forceinline__ float4 conv_src_load(const ConvSrc& s, int b, int plane, int y, int x) {
+  if ((unsigned)y >= (unsigned)s.H || (unsigned)x >= (unsigned)s.W) return f4_zero();
+  if (s.mode == 0) {
+    if (plane < s.p0) {
+      if (s.half0)
+        return __ldg(&s.s0[((size_t)(b * s.p0 + plane) * s.Hh + (y >> 1)) * s.Wh + (x >> 1)]);
+      return __ldg(&s.s0[((size_t)(b * s.p0 + plane) * s.H + y) * s.W + x]);
+    }
+    plane -= s.p0;
+    return __ldg(&s.s1[((size_t)(b * s.p1 + plane) * s.H + y) * s.W + x]);
+  }
+  const int yh = y >> 1, xh = x >> 1;
+  float4 g = __ldg(&s.s0[((size_t)(b * s.p0 + plane) * s.Hh + yh) * s.Wh + xh]);
+  const int cy = (2 * yh + 1 < s.H) ? 2 : 1;
+  const int cx = (2 * xh + 1 < s.W) ? 2 : 1;
+  const float inv = 1.0f / (float)(cy * cx);
+  unsigned bits = __ldg(&s.sign[((size_t)(b * s.p0 + plane) * s.H + y) * s.Wq + (x >> 2)]);
+  bits >>= 4 * (x & 3);
+  g.x = g.x * inv * ((bits & 1u) ? 1.0f : s.slope);
+  g.y = g.y * inv * ((bits & 2u) ? 1.0f : s.slope);
+  g.z = g.z * inv * ((bits & 4u) ? 1.0f : s.slope);
+  g.w = g.w * inv * ((bits & 8u) ? 1.0f : s.slope);
+  return g;
+}
+
+}  // namespace dincae

@@ -1,0 +1,383 @@
+"""Device-side execution plan of the DINCAE network: buffers, parameter layout and the
+sequence of C-ABI kernel calls that replaces the TF-1.15 graph of
+DINCAE/__init__.py:433-603 (encoder, dense bottleneck, decoder, head, loss, gradients,
+clip + Adam).  PyTorch is used only for device memory and streams.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, layout
+from ._lib import check, ptr, stream_ptr
+
+NEG_SLOPE = 0.2          # tf.nn.leaky_relu default alpha (DINCAE/__init__.py:430)
+COUT_ALIGN = 16
+
+
+class Plan:
+    """Static shapes of the network for one (H, W, nvar, filters) configuration."""
+
+    def __init__(self, H, W, nvar=10, enc_nfilter_internal=(16, 24, 36, 54),
+                 frac_dense_layer=(0.2,), skipconnections=(1, 2, 3, 4)):
+        self.H, self.W, self.nvar = int(H), int(W), int(nvar)
+        self.enc_c = [self.nvar] + [int(c) for c in enc_nfilter_internal]
+        self.L = len(self.enc_c) - 1
+        self.dec_c = self.enc_c[:0:-1] + [2]              # index 0..L, like :385
+        self.skip = set(int(s) for s in skipconnections)
+        self.frac = [float(f) for f in frac_dense_layer]
+        self.sizes = [(self.H, self.W)]
+        for _ in range(self.L):
+            h, w = self.sizes[-1]
+            self.sizes.append(((h + 1) // 2, (w + 1) // 2))
+        self.ep = [layout.planes(c) for c in self.enc_c]
+        self.dp = [layout.planes(c) for c in self.dec_c]
+        hL, wL = self.sizes[self.L]
+        self.n_bottleneck = hL * wL * self.enc_c[self.L]
+        self.flat_map, self.n_flat = layout.flat_map(hL, wL, self.enc_c[self.L])
+        if self.frac:
+            fr = self.frac + self.frac[:-1][::-1]
+            self.dense_units = [math.floor(self.n_bottleneck * f) for f in fr] + [self.n_bottleneck]
+        else:
+            self.dense_units = []
+        # padded widths of the dense activations F[0..nd]
+        self.dense_pad = [self.n_flat]
+        for i, u in enumerate(self.dense_units):
+            last = i == len(self.dense_units) - 1
+            self.dense_pad.append(self.n_flat if last else layout.round_up(u, 4))
+        self._build_params()
+
+    # decoder conv l (1..L): sources and sizes -------------------------------------------
+    def dec_sources(self, l):
+        """(channels of upsampled source, channels of skip source or 0, resolution index)."""
+        r = self.L - l                      # output resolution index (= l2 - 1)
+        up = self.dec_c[l - 1]
+        sk = self.enc_c[r] if l in self.skip else 0
+        return up, sk, r
+
+    def _build_params(self):
+        ent = []
+
+        def conv(name, splits, cout):
+            cinp = sum(layout.planes(c) for c in splits)
+            cpad = layout.round_up(cout, COUT_ALIGN)
+            ent.append(dict(name=name + "/kernel", kind="conv_w", tf_shape=(3, 3, sum(splits), cout),
+                            splits=list(splits), cout=cout, cout_pad=cpad, cinp=cinp,
+                            size=9 * cinp * cpad * 4))
+            ent.append(dict(name=name + "/bias", kind="conv_b", tf_shape=(cout,), cout=cout,
+                            size=cpad))
+
+        k = 0
+
+        def cname():
+            nonlocal k
+            n = "conv2d" if k == 0 else "conv2d_%d" % k
+            k += 1
+            return n
+
+        for l in range(1, self.L + 1):
+            conv(cname(), [self.enc_c[l - 1]], self.enc_c[l])
+        nin, nin_pad = self.n_bottleneck, self.n_flat
+        for i, u in enumerate(self.dense_units):
+            name = "dense" if i == 0 else "dense_%d" % i
+            upad = self.dense_pad[i + 1]
+            ent.append(dict(name=name + "/kernel", kind="dense_w", tf_shape=(nin, u),
+                            rows=nin_pad, cols=upad, size=nin_pad * upad, index=i))
+            ent.append(dict(name=name + "/bias", kind="dense_b", tf_shape=(u,), cols=upad,
+                            size=upad, index=i))
+            nin, nin_pad = u, upad
+        for l in range(1, self.L + 1):
+            up, sk, _ = self.dec_sources(l)
+            conv(cname(), [up] + ([sk] if sk else []), self.dec_c[l])
+        # flat layout: all kernels first (they receive the L2 term), then all biases
+        off = 0
+        for e in ent:
+            if e["kind"].endswith("_w"):
+                e["offset"] = off
+                off = layout.round_up(off + e["size"], 64)
+        self.n_decay = off
+        for e in ent:
+            if e["kind"].endswith("_b"):
+                e["offset"] = off
+                off = layout.round_up(off + e["size"], 64)
+        self.n_params_flat = off
+        self.entries = ent
+        self.n_params_tf = sum(int(np.prod(e["tf_shape"])) for e in ent)
+
+    def _dense_maps(self, i):
+        nd = len(self.dense_units)
+        rows = self.flat_map if i == 0 else np.arange(self.dense_units[i - 1])
+        cols = self.flat_map if i == nd - 1 else np.arange(self.dense_units[i])
+        return rows, cols
+
+    def pack(self, tf_params):
+        """List of numpy arrays in TF variable order -> flat float32 vector."""
+        flat = np.zeros(self.n_params_flat, dtype=np.float32)
+        assert len(tf_params) == len(self.entries)
+        for e, p in zip(self.entries, tf_params):
+            p = np.asarray(p, dtype=np.float32)
+            assert tuple(p.shape) == tuple(e["tf_shape"]), (e["name"], p.shape, e["tf_shape"])
+            o, n = e["offset"], e["size"]
+            if e["kind"] == "conv_w":
+                flat[o:o + n] = layout.pack_conv(p, e["splits"], e["cout_pad"]).reshape(-1)
+            elif e["kind"] == "conv_b":
+                flat[o:o + e["cout"]] = p
+            elif e["kind"] == "dense_w":
+                rows, cols = self._dense_maps(e["index"])
+                flat[o:o + n] = layout.pack_dense(p, rows, e["rows"], cols, e["cols"]).reshape(-1)
+            else:
+                _, cols = self._dense_maps(e["index"])
+                flat[o + cols] = p
+        return flat
+
+    def unpack(self, flat):
+        """Flat vector (params or gradients) -> list of numpy arrays in TF order/shape."""
+        out = []
+        flat = np.asarray(flat)
+        for e in self.entries:
+            o, n = e["offset"], e["size"]
+            if e["kind"] == "conv_w":
+                wp = flat[o:o + n].reshape(9, e["cinp"], e["cout_pad"], 4)
+                out.append(layout.unpack_conv(wp, e["splits"], e["cout"]))
+            elif e["kind"] == "conv_b":
+                out.append(flat[o:o + e["cout"]].copy())
+            elif e["kind"] == "dense_w":
+                rows, cols = self._dense_maps(e["index"])
+                out.append(layout.unpack_dense(flat[o:o + n].reshape(e["rows"], e["cols"]), rows, cols))
+            else:
+                _, cols = self._dense_maps(e["index"])
+                out.append(flat[o + cols].copy())
+        return out
+
+    def glorot_init(self, seed):
+        """tf.layers defaults: Glorot-uniform kernels, zero biases."""
+        rs = np.random.RandomState(seed)
+        ps = []
+        for e in self.entries:
+            shp = e["tf_shape"]
+            if e["kind"].endswith("_b"):
+                ps.append(np.zeros(shp, dtype=np.float32))
+                continue
+            if len(shp) == 4:
+                fan_in, fan_out = 9 * shp[2], 9 * shp[3]
+            else:
+                fan_in, fan_out = shp
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            ps.append(rs.uniform(-lim, lim, size=shp).astype(np.float32))
+        return ps
+
+
+class Network:
+    """Buffers + kernel sequences for one Plan on the current CUDA device."""
+
+    def __init__(self, plan, max_batch, train=True, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DincaeError("dincae_b200 needs a CUDA device (no CPU fallback)")
+        self.plan = plan
+        self.Bmax = int(max_batch)
+        self.train = train
+        self.dev = torch.device(device if device is not None else "cuda")
+        P, B, dev = plan, self.Bmax, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        self.params = torch.zeros(P.n_params_flat, **f32)
+        if train:
+            self.grads = torch.zeros(P.n_params_flat, **f32)
+            self.adam_m = torch.zeros(P.n_params_flat, **f32)
+            self.adam_v = torch.zeros(P.n_params_flat, **f32)
+            self.adam_state = torch.zeros(8, **f32)
+            self.lr = torch.zeros(1, **f32)
+            self.reset_optimizer()
+
+        # activations --------------------------------------------------------------------
+        self.X = [torch.zeros(B, P.ep[k], P.sizes[k][0], P.sizes[k][1], 4, **f32)
+                  for k in range(P.L + 1)]
+        self.xtrue = torch.zeros(B, P.H, P.W, 2, **f32)
+        self.n_noncloud = torch.zeros(1, dtype=torch.int32, device=dev)
+        nd = len(P.dense_units)
+        self.F = [self.X[P.L].view(B, -1)]
+        for i in range(nd):
+            self.F.append(torch.zeros(B, P.dense_pad[i + 1], **f32))
+        self.D = [self.F[-1].view(B, P.ep[P.L], P.sizes[P.L][0], P.sizes[P.L][1], 4)]
+        for l in range(1, P.L + 1):
+            h, w = P.sizes[P.L - l]
+            self.D.append(torch.zeros(B, P.dp[l], h, w, 4, **f32))
+        self.m_rec = torch.zeros(B, P.H, P.W, **f32)
+        self.s2_rec = torch.zeros(B, P.H, P.W, **f32)
+
+        ws = [self.lib.dincae_dense_workspace(B, P.dense_pad[i], P.dense_pad[i + 1])
+              for i in range(nd)]
+        if train:
+            self.S = [None] + [
+                torch.zeros(B, P.ep[l], P.sizes[l - 1][0], (P.sizes[l - 1][1] + 3) // 4,
+                            dtype=torch.int16, device=dev) for l in range(1, P.L + 1)]
+            self.GD = [torch.zeros_like(d) for d in self.D]           # dZ of decoder convs / dense out
+            self.dX = [None] + [torch.zeros_like(self.X[k]) for k in range(1, P.L + 1)]
+            self.dXskip = [None] * (P.L + 1)
+            for l in range(1, P.L + 1):
+                _, sk, r = P.dec_sources(l)
+                if sk and r >= 1:
+                    self.dXskip[r] = torch.zeros_like(self.X[r])
+            self.dZ = [None] + [torch.zeros_like(self.F[i + 1]) for i in range(nd)]
+            if nd:
+                self.dZ[nd] = self.GD[0].view(B, -1)
+            self.loss_sums = torch.zeros(4, dtype=torch.float64, device=dev)
+            self.loss_out = torch.zeros(2, **f32)
+            self.l2_out = torch.zeros(1, **f32)
+            ws.append(self.lib.dincae_head_loss_workspace(B, P.H, P.W))
+            ws.append(self.lib.dincae_adam_workspace(P.n_params_flat))
+            for e in P.entries:
+                if e["kind"] == "conv_w":
+                    h, w = self._conv_res(e)
+                    ws.append(self.lib.dincae_conv3x3_wgrad_workspace(e["cinp"], 0, e["cout_pad"], B, h, w))
+        self.workspace = torch.zeros(max(ws + [256]), dtype=torch.uint8, device=dev)
+        self._ent = {e["name"]: e for e in P.entries}
+        self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
+
+    # ---- parameters -----------------------------------------------------------------------
+    def _conv_res(self, e):
+        idx = [x["name"] for x in self.plan.entries if x["kind"] == "conv_w"].index(e["name"])
+        L = self.plan.L
+        return self.plan.sizes[idx] if idx < L else self.plan.sizes[L - (idx - L + 1)]
+
+    def reset_optimizer(self, beta1=0.9, beta2=0.999):
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        self.adam_state.zero_()
+        self.adam_state[0] = beta1
+        self.adam_state[1] = beta2
+
+    def set_params_tf(self, tf_params):
+        self.params.copy_(torch.from_numpy(self.plan.pack(tf_params)))
+
+    def get_params_tf(self):
+        return self.plan.unpack(self.params.cpu().numpy())
+
+    def get_grads_tf(self):
+        return self.plan.unpack(self.grads.cpu().numpy())
+
+    def _w(self, name, buf=None):
+        e = self._ent[name]
+        buf = self.params if buf is None else buf
+        return buf[e["offset"]: e["offset"] + e["size"]]
+
+    def _enc_name(self, l):
+        return self._conv_names[l - 1]
+
+    def _dec_name(self, l):
+        return self._conv_names[self.plan.L + l - 1]
+
+    # ---- forward --------------------------------------------------------------------------
+    def forward(self, B, save_signs=None):
+        """Encoder -> dense -> decoder on self.X[0][:B]; leaves xrec in self.D[L]."""
+        P, lib, st = self.plan, self.lib, stream_ptr()
+        save_signs = self.train if save_signs is None else save_signs
+        for l in range(1, P.L + 1):
+            h, w = P.sizes[l - 1]
+            e = self._ent[self._enc_name(l) + "/kernel"]
+            check(lib.dincae_conv3x3_fwd(
+                ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
+                ptr(self._w(e["name"])), ptr(self._w(self._enc_name(l) + "/bias")), e["cout_pad"],
+                B, h, w, P.ep[l], NEG_SLOPE, None, ptr(self.X[l]),
+                ptr(self.S[l]) if save_signs else None, st), "conv3x3_fwd(enc %d)" % l)
+        for i in range(len(P.dense_units)):
+            name = "dense" if i == 0 else "dense_%d" % i
+            check(lib.dincae_dense_fwd(
+                ptr(self.F[i]), ptr(self._w(name + "/kernel")), ptr(self._w(name + "/bias")),
+                B, P.dense_pad[i], P.dense_pad[i + 1], 1, ptr(self.F[i + 1]),
+                ptr(self.workspace), self.workspace.numel(), st), "dense_fwd(%d)" % i)
+        for l in range(1, P.L + 1):
+            up, sk, r = P.dec_sources(l)
+            h, w = P.sizes[r]
+            e = self._ent[self._dec_name(l) + "/kernel"]
+            check(lib.dincae_conv3x3_fwd(
+                ptr(self.D[l - 1]), P.dp[l - 1] if l > 1 else P.ep[P.L], 1,
+                ptr(self.X[r]) if sk else None, P.ep[r] if sk else 0,
+                ptr(self._w(e["name"])), ptr(self._w(self._dec_name(l) + "/bias")), e["cout_pad"],
+                B, h, w, P.dp[l], NEG_SLOPE, ptr(self.D[l]), None, None, st),
+                "conv3x3_fwd(dec %d)" % l)
+
+    def head_recon(self, B):
+        P = self.plan
+        check(self.lib.dincae_head_recon(ptr(self.D[P.L]), B, P.H, P.W, ptr(self.m_rec),
+                                         ptr(self.s2_rec), stream_ptr()), "head_recon")
+
+    # ---- loss + backward --------------------------------------------------------------------
+    def loss_backward(self, B, truth_uncertain=False, normalise=True):
+        """head + NLL, then gradients of every parameter into self.grads."""
+        P, lib, st = self.plan, self.lib, stream_ptr()
+        L = P.L
+        wsp, wsn = ptr(self.workspace), self.workspace.numel()
+        check(lib.dincae_head_loss(
+            ptr(self.D[L]), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
+            ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self.loss_sums),
+            ptr(self.loss_out), wsp, wsn, st), "head_loss")
+        has_dense = len(P.dense_units) > 0
+        for l in range(L, 0, -1):
+            up, sk, r = P.dec_sources(l)
+            h, w = P.sizes[r]
+            name = self._dec_name(l)
+            e = self._ent[name + "/kernel"]
+            c0p = P.dp[l - 1] if l > 1 else P.ep[L]
+            c1p = P.ep[r] if sk else 0
+            check(lib.dincae_conv3x3_wgrad(
+                ptr(self.D[l - 1]), c0p, 1, ptr(self.X[r]) if sk else None, c1p,
+                ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l], e["cout_pad"], B, h, w,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                wsp, wsn, st), "conv3x3_wgrad(dec %d)" % l)
+            prev_slope = NEG_SLOPE if l > 1 else (0.0 if has_dense else 1.0)
+            want_skip = bool(sk) and r >= 1
+            check(lib.dincae_conv3x3_dgrad(
+                ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l],
+                ptr(self._w(name + "/kernel")), e["cinp"], e["cout_pad"], B, h, w,
+                c0p, ptr(self.D[l - 1]), prev_slope, ptr(self.GD[l - 1]),
+                c1p if want_skip else 0, ptr(self.dXskip[r]) if want_skip else None, None, st),
+                "conv3x3_dgrad(dec %d)" % l)
+        nd = len(P.dense_units)
+        for i in range(nd - 1, -1, -1):
+            name = "dense" if i == 0 else "dense_%d" % i
+            K, N = P.dense_pad[i], P.dense_pad[i + 1]
+            check(lib.dincae_dense_bwd_weight(
+                ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                st), "dense_bwd_weight(%d)" % i)
+            dst = self.dZ[i] if i > 0 else self.dX[L].view(self.Bmax, -1)
+            check(lib.dincae_dense_bwd_data(
+                ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
+                ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
+                "dense_bwd_data(%d)" % i)
+        top_grad = self.dX[L] if has_dense else self.GD[0]
+        for l in range(L, 0, -1):
+            h, w = P.sizes[l - 1]
+            name = self._enc_name(l)
+            e = self._ent[name + "/kernel"]
+            gpool = top_grad if l == L else self.dX[l]
+            check(lib.dincae_conv3x3_wgrad(
+                ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
+                None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l], e["cout_pad"], B, h, w,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                wsp, wsn, st), "conv3x3_wgrad(enc %d)" % l)
+            if l > 1:
+                check(lib.dincae_conv3x3_dgrad(
+                    None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l],
+                    ptr(self._w(name + "/kernel")), e["cinp"], e["cout_pad"], B, h, w,
+                    0, None, 1.0, None,
+                    P.ep[l - 1], ptr(self.dX[l - 1]),
+                    ptr(self.dXskip[l - 1]) if self.dXskip[l - 1] is not None else None, st),
+                    "conv3x3_dgrad(enc %d)" % l)
+
+    def l2_value(self):
+        """0.5 * sum of squares of all kernels -> self.l2_out (device)."""
+        check(self.lib.dincae_l2_half_sumsq(ptr(self.params), self.plan.n_decay, ptr(self.l2_out),
+                                            ptr(self.workspace), self.workspace.numel(),
+                                            stream_ptr()), "l2_half_sumsq")
+
+    def adam_step(self, clip_norm=5.0, l2_beta=0.0, beta1=0.9, beta2=0.999, eps=1e-8,
+                  grad_scale=1.0, denom=None):
+        """clip_by_global_norm + Adam on self.grads; learning rate read from self.lr."""
+        check(self.lib.dincae_adam_step(
+            ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
+            self.plan.n_params_flat, self.plan.n_decay, l2_beta, clip_norm, ptr(self.lr),
+            beta1, beta2, eps, grad_scale, ptr(denom), ptr(self.adam_state),
+            ptr(self.workspace), self.workspace.numel(), stream_ptr()), "adam_step")

@@ -1,0 +1,220 @@
+"""Training / reconstruction driver on top of engine.Network and data.DeviceCube.
+
+One ``Trainer.train_step`` = one ``sess.run([cost, RMS, opt])`` of the reference
+(DINCAE/__init__.py:649-654): batch assembly, forward, loss, backward, global-norm clip and
+Adam -- all on the device, captured once into a CUDA graph and replayed.  Per step the host
+sends 16 bytes per frame of indices and reads back 40 bytes of loss sums.
+
+Data parallelism (new capability): one process per GPU; every rank
+draws the same global index stream and builds its own slice; gradients and the loss sums
+are left un-normalised, summed with an NCCL all-reduce, and divided by the global count of
+observed pixels inside the Adam kernel, so N ranks x B frames is numerically a single
+batch of N*B.
+"""
+import numpy as np
+import torch
+
+from .engine import Network
+
+
+class Trainer:
+    def __init__(self, plan, cube, batch_size, truth_uncertain=False, clip_grad=5.0,
+                 l2_beta=0.0, noise_seed=0, use_graph=True, dist_group=None, tf_params=None,
+                 init_seed=0, jitter_std=None):
+        self.plan, self.cube = plan, cube
+        self.B = int(batch_size)
+        self.truth_uncertain = bool(truth_uncertain)
+        self.clip_grad = float(clip_grad)
+        self.l2_beta = float(l2_beta)
+        self.noise_seed = int(noise_seed)
+        self.jitter_std = jitter_std
+        self.net = Network(plan, self.B, train=True, device=cube.dev)
+        self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
+        self.dist = None
+        self.rank, self.world = 0, 1
+        if dist_group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.group = dist_group if dist_group is not True else None
+            self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+            dist.broadcast(self.net.params, src=0, group=self.group)
+        dev = cube.dev
+        B = self.B
+        # [frame(B) | cloud(B) | seq int64 (2B int32)]
+        self.idx_host = torch.zeros(4 * B, dtype=torch.int32).pin_memory()
+        self.idx_dev = torch.zeros(4 * B, dtype=torch.int32, device=dev)
+        self.frame_idx = self.idx_dev[:B]
+        self.cloud_idx = self.idx_dev[B:2 * B]
+        self.noise_seq = self.idx_dev[2 * B:].view(torch.int64)
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._ring = torch.zeros(1024, 4, dtype=torch.float64).pin_memory()
+        self._ring_l2 = torch.zeros(1024, 1, dtype=torch.float32).pin_memory()
+        self._pending = []          # ring slots not yet converted to floats
+        self._ring_pos = 0
+        self.step_count = 0
+        self.launches_per_step = None
+
+    # ---- one optimisation step ---------------------------------------------------------------
+    def _enqueue_fwd_bwd(self):
+        net, B = self.net, self.B
+        net.n_noncloud.zero_()
+        self.cube.build_batch(self.frame_idx, self.cloud_idx, B, net.X[0], net.xtrue,
+                              net.n_noncloud, jitter_std=self.jitter_std, seed=self.noise_seed,
+                              noise_seq=self.noise_seq)
+        net.forward(B)
+        net.loss_backward(B, self.truth_uncertain, normalise=False)
+        if self.l2_beta != 0.0:
+            net.l2_value()
+
+    def _enqueue_update(self):
+        net = self.net
+        net.adam_step(clip_norm=self.clip_grad, l2_beta=self.l2_beta, denom=net.loss_sums[3:4])
+
+    def _run(self, key, fn):
+        if not self.use_graph:
+            fn()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            # warm up on a side stream (required before capture), then capture
+            s = torch.cuda.Stream(device=self.cube.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._snapshot()
+                fn()
+                self._restore()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+        g.replay()
+
+    def _snapshot(self):
+        n = self.net
+        self._snap = [t.clone() for t in (n.params, n.adam_m, n.adam_v, n.adam_state)]
+
+    def _restore(self):
+        n = self.net
+        for t, s in zip((n.params, n.adam_m, n.adam_v, n.adam_state), self._snap):
+            t.copy_(s)
+        self._snap = None
+
+    def set_lr(self, lr):
+        self.net.lr.fill_(float(lr))
+
+    def upload_indices(self, frame_idx, cloud_idx, seq):
+        B = self.B
+        h = self.idx_host
+        h[:B] = torch.from_numpy(np.ascontiguousarray(frame_idx, dtype=np.int32))
+        h[B:2 * B] = torch.from_numpy(np.ascontiguousarray(cloud_idx, dtype=np.int32))
+        h[2 * B:].view(torch.int64)[:] = torch.from_numpy(np.ascontiguousarray(seq, dtype=np.int64))
+        self.idx_dev.copy_(h, non_blocking=True)
+
+    def train_step(self, frame_idx, cloud_idx, seq):
+        """Enqueue one step for this rank's B frames; the loss is fetched lazily."""
+        self.upload_indices(frame_idx, cloud_idx, seq)
+        if self.dist is None:
+            self._run("step", lambda: (self._enqueue_fwd_bwd(), self._enqueue_update()))
+        else:
+            self._run("fwd_bwd", self._enqueue_fwd_bwd)
+            self.dist.all_reduce(self.net.grads, group=self.group)
+            self.dist.all_reduce(self.net.loss_sums, group=self.group)
+            self._run("update", self._enqueue_update)
+        # loss bookkeeping: 4 sums + L2 value -> pinned ring (async)
+        slot = self._ring_pos % self._ring.shape[0]
+        if len(self._pending) >= self._ring.shape[0] - 1:
+            self.flush_losses()
+        self._ring[slot].copy_(self.net.loss_sums, non_blocking=True)
+        if self.l2_beta != 0.0:
+            self._ring_l2[slot].copy_(self.net.l2_out, non_blocking=True)
+        self._pending.append(slot)
+        self._ring_pos += 1
+        self.step_count += 1
+
+    def flush_losses(self):
+        """Synchronise and return [(cost, RMS), ...] of the steps since the last flush."""
+        if not self._pending:
+            return []
+        torch.cuda.current_stream().synchronize()
+        out = []
+        for slot in self._pending:
+            s = self._ring[slot].numpy()
+            n = s[3]
+            cost = (s[0] + s[1]) / n if n != 0 else float("nan")
+            if self.l2_beta != 0.0:
+                cost = cost + self.l2_beta * float(self._ring_l2[slot, 0])
+            rms = float(np.sqrt(s[2] / n)) if n != 0 else float("nan")
+            out.append((float(np.float32(cost)), float(np.float32(rms))))
+        self._pending = []
+        return out
+
+
+class Reconstructor:
+    """Forward-only sweep (DINCAE/__init__.py:678-689): test-mode batches, head, D2H."""
+
+    def __init__(self, plan, cube, batch_size, net=None, train_mode_inputs=False, noise_seed=0,
+                 use_graph=True, py_random=None, jitter_std=None):
+        self.plan, self.cube, self.B = plan, cube, int(batch_size)
+        self.net = net if net is not None else Network(plan, self.B, train=False, device=cube.dev)
+        self.train_mode_inputs = train_mode_inputs       # reference quirk Q1
+        self.noise_seed = noise_seed
+        self.jitter_std = jitter_std
+        self.use_graph = use_graph
+        self.py_random = py_random
+        dev = cube.dev
+        B = self.B
+        self.idx_host = torch.zeros(4 * B, dtype=torch.int32).pin_memory()
+        self.idx_dev = torch.zeros(4 * B, dtype=torch.int32, device=dev)
+        self.out_host = [torch.zeros(2, B, plan.H, plan.W).pin_memory() for _ in range(2)]
+        self.out_dev = torch.zeros(2, B, plan.H, plan.W, device=dev)
+        self._graphs = {}
+        self._seq = 0
+
+    def _enqueue(self, n):
+        net, B = self.net, self.B
+        net.n_noncloud.zero_()
+        cloud = self.idx_dev[B:2 * B] if self.train_mode_inputs else None
+        self.cube.build_batch(self.idx_dev[:B], cloud, n, net.X[0], net.xtrue, net.n_noncloud,
+                              jitter_std=self.jitter_std, seed=self.noise_seed, noise_seq=self.idx_dev[2 * B:].view(torch.int64))
+        net.forward(n, save_signs=False)
+        net.head_recon(n)
+        self.out_dev[0, :n].copy_(net.m_rec[:n])
+        self.out_dev[1, :n].copy_(net.s2_rec[:n])
+
+    def run_batch(self, frames, slot=0):
+        """frames: int array (n <= B).  Returns pinned host tensor [2,B,H,W] (valid after a
+        stream sync): [0] = m_rec, [1] = sigma2_rec."""
+        n, B = len(frames), self.B
+        h = self.idx_host
+        h[:n] = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.int32))
+        if self.train_mode_inputs:
+            import random as _r
+            rnd = self.py_random or _r
+            T = self.cube.T
+            h[B:B + n] = torch.tensor([rnd.randrange(0, T) for _ in range(n)], dtype=torch.int32)
+            seq = torch.arange(self._seq, self._seq + n, dtype=torch.int64)
+            h[2 * B:].view(torch.int64)[:n] = seq
+            self._seq += n
+        self.idx_dev.copy_(h, non_blocking=True)
+        if self.use_graph:
+            g = self._graphs.get(n)
+            if g is None:
+                s = torch.cuda.Stream(device=self.cube.dev)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._enqueue(n)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(n)
+                self._graphs[n] = g
+            g.replay()
+        else:
+            self._enqueue(n)
+        out = self.out_host[slot]
+        out.copy_(self.out_dev, non_blocking=True)
+        return out

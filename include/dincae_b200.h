@@ -1,0 +1,198 @@
+/*
+ * dincae_b200 -- C ABI of the B200 (sm_100a) kernels behind DINCAE's train + reconstruct
+ * hot path.  Every entry point replaces a block of the TensorFlow-1.15 graph (or of the
+ * numpy input pipeline) that the reference builds in DINCAE/__init__.py; the citation on
+ * each declaration is the reference interface it stands in for.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - All data pointers are DEVICE pointers owned by the caller unless marked "host".
+ *   - Nothing here allocates, synchronises the device or keeps global state; every call
+ *     only enqueues work on `stream` (a cudaStream_t passed as void*), so sequences of
+ *     calls can be captured into a CUDA graph.
+ *   - Return value: 0 on success, a negative DINCAE_E* code otherwise
+ *     (dincae_error_string() names it; dincae_last_cuda_error() gives the CUDA code).
+ *
+ * Activation layout ("planar-4", P4): a tensor with C channels at spatial size H x W is
+ * stored as float [B][CP][H][W][4] with CP = ceil(C/4) channel planes; channel c lives in
+ * plane c/4, lane c%4; lanes past C are zero.  A concatenation of two tensors is never
+ * materialised: kernels take two sources.  A "half" source is stored at
+ * (ceil(H/2), ceil(W/2)) and read at (y>>1, x>>1) == TF1 legacy nearest-neighbour resize
+ * for the sizes this network produces (DINCAE/__init__.py:496-499).
+ *
+ * Conv weight layout ("WP"): float [9][CinP][CoutPad][4]: tap t = 3*ky+kx, input plane,
+ * output channel (padded to CoutPad, a multiple of 4), 4 input lanes.  TF's HWIO kernel
+ * [3,3,Cin,Cout] maps to it by dincae_b200.layout.pack_conv (host, init/export only).
+ * Sign masks: uint16 [B][CP][H][ceil(W/4)], bit 4*(x%4)+lane set when the conv
+ * pre-activation was > 0 (what LeakyReluGrad needs, instead of the full-res activation).
+ */
+#ifndef DINCAE_B200_H
+#define DINCAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DINCAE_OK 0
+#define DINCAE_EINVAL (-1)   /* bad argument (null pointer, non-positive size, ...) */
+#define DINCAE_ECUDA (-2)    /* a CUDA runtime call / launch failed */
+#define DINCAE_ENOSPC (-3)   /* caller-provided workspace too small */
+#define DINCAE_EARCH (-4)    /* device is not sm_100 */
+
+const char* dincae_version(void);
+const char* dincae_error_string(int code);
+int dincae_last_cuda_error(void);
+/* sm_count, compute capability of the current device. */
+int dincae_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- input pipeline ---------------------------------------------------------------- */
+
+/* Temporal-mean removal, DINCAE/__init__.py:167-169,180 (data_generator_list pre-pass).
+ * data[T,H,W] f32, missing[T,H,W] u8 (1 = masked).  Writes
+ *   meandata[H,W] f64 = (f32 running sum over valid t) * 1. / count   (numpy MaskedArray.mean)
+ *   never[H,W]    u8  = 1 where count == 0 (meandata.mask)
+ *   anom[T,H,W]   f32 = f32(((f64)data - meandata) / obs_var), 0 where missing.
+ * nomask != 0 selects numpy's ndarray.mean path for an input without a mask (f32 mean). */
+int dincae_prepare_cube(const float* data, const uint8_t* missing, int T, int H, int W,
+                        double obs_var, int nomask,
+                        float* anom, double* meandata, uint8_t* never, void* stream);
+
+/* One mini-batch of network inputs, DINCAE/__init__.py:196-227 (closure datagen) plus the
+ * tf.data batching of :399-401.  For b < B, frame i = frame_idx[b]:
+ *   xin  P4 [B][nvarP][H][W][4]: channels [ (anom_j, invvar_j) j<ndata | lon lat cos sin |
+ *        (anom_j, invvar_j) at clamp(i+nn) for each nn != 0 of the time window ]
+ *   xtrue [B][H][W][2] = channels 0,1 of the UNPERTURBED frame.
+ * cloud_idx != NULL (train mode): where cloud_missing[j][cloud_idx[b]] is set (the `missing`
+ *   argument of the reference generator; NULL = same array as `missing`), channels 2j,2j+1
+ *   of the current frame are zeroed (:214-219); then jitter is added to channels 2j,
+ *   2j+2nd+4, 2j+4nd+4 (:222-225): from noise[B][3*ndata][H][W] (f64 standard normals in the
+ *   reference's draw order; x = f32((f64)x + jitter_std[j]*noise), bit-exact parity mode)
+ *   or, if noise == NULL, from Philox4x32-10 keyed by (seed, noise_seq[b], pixel).
+ * n_noncloud (int32, device) is incremented by the number of xtrue[...,1] != 0 (:541-544).
+ * anom/missing: [ndata][T][H][W]; inv_var, jitter_std: host arrays of ndata doubles. */
+int dincae_build_batch(const float* anom, const uint8_t* missing,
+                       const uint8_t* cloud_missing,
+                       const float* lon_scaled, const float* lat_scaled,
+                       const float* doy_cos, const float* doy_sin,
+                       const double* inv_var_host, const double* jitter_std_host,
+                       int ndata, int T, int H, int W, int ntime_win,
+                       const int32_t* frame_idx, const int32_t* cloud_idx, int B,
+                       const double* noise, uint64_t seed, const int64_t* noise_seq,
+                       float* xin, int nvar_planes, float* xtrue, int32_t* n_noncloud,
+                       void* stream);
+
+/* ---- 3x3 convolutions -------------------------------------------------------------- */
+
+/* tf.layers.conv2d(3x3, SAME) + leaky_relu [+ average_pooling2d(2,2,SAME)],
+ * DINCAE/__init__.py:442-452 (encoder) and :496-513 (decoder: resize + concat + conv).
+ * Input = concat(src0 [c0p planes; half-res if src0_half], src1 [c1p planes, may be NULL]).
+ * Outputs (any may be NULL): out_full P4 [B][coutp][H][W][4] activated;
+ * out_pool P4 at (ceil(H/2),ceil(W/2)) = SAME avg-pool of the activated output (padding
+ * excluded from the divisor); out_sign = sign mask of the pre-activation. */
+int dincae_conv3x3_fwd(const float* src0, int c0p, int src0_half,
+                       const float* src1, int c1p,
+                       const float* wpack, const float* bias, int cout_pad,
+                       int B, int H, int W, int coutp, float neg_slope,
+                       float* out_full, float* out_pool, uint16_t* out_sign,
+                       void* stream);
+
+/* Conv2DBackpropInput with the neighbouring pointwise gradients fused
+ * (what optimizer.compute_gradients builds for :442-452 / :496-513).
+ * Incoming gradient G w.r.t. the conv PRE-activation, gp planes at H x W, given either as
+ *   g_full  P4 [B][gp][H][W][4], or
+ *   g_pool  P4 at half res + sign: G = g_pool[y>>1][x>>1] / window_count * (sign ? 1 : neg_slope)
+ *           (AvgPoolGrad followed by LeakyReluGrad of an encoder stage).
+ * dU = G (*) W^T over the conv's cin planes, of which
+ *   planes [0, c_lo)      (the half-res source): summed over each 2x2 block
+ *                          (ResizeNearestNeighborGrad), multiplied by
+ *                          (prev_act > 0 ? 1 : prev_slope) and written to g_prev
+ *                          P4 [B][c_lo][ceil(H/2)][ceil(W/2)][4];  prev_act may be NULL (factor 1);
+ *   planes [c_lo, c_lo+c_hi): written full-res to dx_hi P4 [B][c_hi][H][W][4], plus dx_add
+ *                          (same shape) if not NULL.  c_hi == 0 skips them entirely. */
+int dincae_conv3x3_dgrad(const float* g_full, const float* g_pool, const uint16_t* sign,
+                         float neg_slope, int gp,
+                         const float* wpack, int cinp, int cout_pad,
+                         int B, int H, int W,
+                         int c_lo, const float* prev_act, float prev_slope, float* g_prev,
+                         int c_hi, float* dx_hi, const float* dx_add,
+                         void* stream);
+
+/* Conv2DBackpropFilter + BiasAddGrad.  Same input description as conv3x3_fwd and same
+ * gradient description as conv3x3_dgrad.  dw in WP layout [9][c0p+c1p][cout_pad][4],
+ * db [cout_pad].  Deterministic two-stage reduction through `workspace`
+ * (dincae_conv3x3_wgrad_workspace() bytes). */
+size_t dincae_conv3x3_wgrad_workspace(int c0p, int c1p, int cout_pad, int B, int H, int W);
+int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half,
+                         const float* src1, int c1p,
+                         const float* g_full, const float* g_pool, const uint16_t* sign,
+                         float neg_slope, int gp, int cout_pad,
+                         int B, int H, int W,
+                         float* dw, float* db, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- dense bottleneck -------------------------------------------------------------- */
+
+/* tf.layers.dense(activation=relu), DINCAE/__init__.py:479-483 (dropout is inert there).
+ * y[B,N] = act(x[B,K] w[K,N] + bias[N]); relu != 0 applies max(.,0). */
+size_t dincae_dense_workspace(int B, int K, int N);
+int dincae_dense_fwd(const float* x, const float* w, const float* bias, int B, int K, int N,
+                     int relu, float* y, void* workspace, size_t workspace_bytes, void* stream);
+/* dx[B,K] = (dz[B,N] w^T) * (act_in > 0) (act_in NULL: no mask)  -- MatMul grad + ReluGrad. */
+int dincae_dense_bwd_data(const float* dz, const float* w, const float* act_in,
+                          int B, int K, int N, float* dx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* dw[K,N] = x^T dz, db[N] = sum_b dz. */
+int dincae_dense_bwd_weight(const float* x, const float* dz, int B, int K, int N,
+                            float* dw, float* db, void* stream);
+
+/* ---- output head, loss ------------------------------------------------------------- */
+
+/* DINCAE/__init__.py:520-523 + sinv :298-299: xrec P4 [B][1][H][W][4] (lanes 0,1) ->
+ * m_rec, sigma2_rec [B][H][W]. */
+int dincae_head_recon(const float* xrec, int B, int H, int W,
+                      float* m_rec, float* sigma2_rec, void* stream);
+
+/* Masked Gaussian NLL (or its truth_uncertain KL variant), RMS and the gradient w.r.t.
+ * the last conv's pre-activation, DINCAE/__init__.py:520-570 and their TF gradients.
+ * n_noncloud: device int32 normaliser n of :544, or NULL.  With NULL the gradient is left
+ *   UN-normalised (n := 1) so that data-parallel ranks can sum gradients and counts first;
+ *   dincae_adam_step() then divides by the reduced count (its `denom` argument).
+ * g_out P4 [B][1][H][W][4] = dcost/dxrec * (xrec > 0 ? 1 : neg_slope), lanes 2,3 zero.
+ * sums (device, 4 doubles) receives [sum w log s2 (+KL terms), sum w d^2/s2, sum w d^2, sum w];
+ * loss_out (device, 2 floats) = [cost, RMS] from these sums over n (n = sum w when
+ *   n_noncloud is NULL).
+ * workspace: dincae_head_loss_workspace() bytes. */
+size_t dincae_head_loss_workspace(int B, int H, int W);
+int dincae_head_loss(const float* xrec, const float* xtrue, int B, int H, int W,
+                     int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
+                     float* g_out, double* sums, float* loss_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimizer --------------------------------------------------------------------- */
+
+/* tf.clip_by_global_norm + tf.train.AdamOptimizer.apply_gradients (+ the gradient of the
+ * optional L2 term), DINCAE/__init__.py:563-567, 598-603.
+ * params/grads/m/v: flat f32 arrays of n entries; the first n_decay entries are the
+ * "kernel" variables that receive g += l2_beta * p before clipping.
+ * state (device, 8 floats): [0] beta1^t, [1] beta2^t (initialise to beta1, beta2),
+ * [2] global norm of this step, [3] lr_t, [4] clip scale; lr: device float.
+ * grads are first multiplied by grad_scale and, if denom (device double) is not NULL, divided
+ * by *denom (the all-reduced count of observed pixels, see dincae_head_loss). */
+size_t dincae_adam_workspace(size_t n);
+int dincae_adam_step(float* params, const float* grads, float* m, float* v,
+                     size_t n, size_t n_decay, float l2_beta, float clip_norm,
+                     const float* lr, float beta1, float beta2, float eps, float grad_scale,
+                     const double* denom, float* state, void* workspace, size_t workspace_bytes, void* stream);
+
+/* 0.5 * sum p^2 over the first n_decay params -> out (device float): value of the L2 term
+ * of the reported cost (:565-567), multiplied by l2_beta by the caller. */
+int dincae_l2_half_sumsq(const float* params, size_t n_decay, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINCAE_B200_H */

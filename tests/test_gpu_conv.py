@@ -1,0 +1,211 @@
+"""3x3 conv kernels (forward / data gradient / weight gradient, with the fused pool,
+upsample, concat and activation gradients) vs PyTorch-CPU autograd of the TF graph blocks
+DINCAE/__init__.py:442-452 and :496-513.  fp32 FFMA path: tolerance 2e-5 of the max."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dincae_b200 import _lib, layout
+from dincae_b200._lib import check, ptr
+from tests.util import dev, from_p4, p4, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+SLOPE = 0.2
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1)
+
+
+def conv_ref(u, k, b=None):
+    return nhwc(F.conv2d(nchw(u), k.permute(3, 2, 0, 1), b, padding=1))
+
+
+def pool_ref(a):
+    return nhwc(F.avg_pool2d(nchw(a), 2, 2, ceil_mode=True, count_include_pad=False))
+
+
+def up_ref(d, size):
+    return nhwc(F.interpolate(nchw(d), size=size, mode="nearest"))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+ENC_CASES = [(2, 12, 20, 10, 16), (3, 15, 11, 16, 24), (2, 7, 7, 36, 54), (1, 112, 112, 10, 16),
+             (2, 33, 70, 5, 3)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", ENC_CASES)
+def test_encoder_stage_forward_and_backward(B, H, W, Cin, Cout):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    k = torch.randn(3, 3, Cin, Cout, generator=g) * 0.2
+    b = torch.randn(Cout, generator=g) * 0.1
+    Hh, Wh = (H + 1) // 2, (W + 1) // 2
+    gpool = torch.randn(B, Hh, Wh, Cout, generator=g)
+    dx_add = torch.randn(B, H, W, Cin, generator=g)
+
+    xr = x.clone().requires_grad_(True)
+    kr = k.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    z = conv_ref(xr, kr, br)
+    a = F.leaky_relu(z, SLOPE)
+    pooled = pool_ref(a)
+    (pooled * gpool).sum().backward()
+
+    cinp, coutp = layout.planes(Cin), layout.planes(Cout)
+    cpad = layout.round_up(Cout, 16)
+    wp = dev(layout.pack_conv(k.numpy(), [Cin], cpad))
+    bias = torch.zeros(cpad, device="cuda")
+    bias[:Cout] = b.cuda()
+    xd = p4(x.numpy())
+    out_full = torch.zeros(B, coutp, H, W, 4, device="cuda")
+    out_pool = torch.zeros(B, coutp, Hh, Wh, 4, device="cuda")
+    out_sign = torch.zeros(B, coutp, H, (W + 3) // 4, dtype=torch.int16, device="cuda")
+    check(lib.dincae_conv3x3_fwd(ptr(xd), cinp, 0, None, 0, ptr(wp), ptr(bias), cpad, B, H, W,
+                                 coutp, SLOPE, ptr(out_full), ptr(out_pool), ptr(out_sign), stream()))
+    torch.cuda.synchronize()
+    assert rel_err(from_p4(out_full, Cout), a.detach().numpy()) < TOL
+    assert rel_err(from_p4(out_pool, Cout), pooled.detach().numpy()) < TOL
+    # padded lanes stay exactly zero
+    if Cout % 4:
+        assert float(out_pool[:, -1, :, :, Cout % 4:].abs().max()) == 0.0
+    # sign mask: exact except where |z| is at rounding level
+    want_sign = layout.sign_mask(z.detach().numpy())
+    got_sign = out_sign.cpu().numpy().view(np.uint16)
+    diff = want_sign ^ got_sign
+    zmin = np.abs(z.detach().numpy())
+    assert np.count_nonzero(diff) <= np.count_nonzero(zmin < 1e-5)
+
+    # backward through pool + leaky relu (sign mask from the kernel itself)
+    gp = p4(gpool.numpy())
+    dx = torch.zeros(B, cinp, H, W, 4, device="cuda")
+    add = p4(dx_add.numpy())
+    check(lib.dincae_conv3x3_dgrad(None, ptr(gp), ptr(out_sign), SLOPE, coutp, ptr(wp), cinp, cpad,
+                                   B, H, W, 0, None, 1.0, None, cinp, ptr(dx), ptr(add), stream()))
+    ws_bytes = lib.dincae_conv3x3_wgrad_workspace(cinp, 0, cpad, B, H, W)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((9, cinp, cpad, 4), 7.0, device="cuda")
+    db = torch.full((cpad,), 7.0, device="cuda")
+    check(lib.dincae_conv3x3_wgrad(ptr(xd), cinp, 0, None, 0, None, ptr(gp), ptr(out_sign), SLOPE,
+                                   coutp, cpad, B, H, W, ptr(dw), ptr(db), ptr(ws), ws_bytes, stream()))
+    torch.cuda.synchronize()
+    assert rel_err(from_p4(dx, Cin), (xr.grad + dx_add).numpy()) < TOL
+    assert rel_err(layout.unpack_conv(dw.cpu().numpy(), [Cin], Cout), kr.grad.numpy()) < TOL
+    assert rel_err(db.cpu().numpy()[:Cout], br.grad.numpy()) < TOL
+    # padding of the packed gradient is exactly zero (keeps padded weights at zero forever)
+    full = dw.cpu().numpy().copy()
+    idx, _ = layout.cin_map([Cin])
+    full[:, idx // 4, :Cout, idx % 4] = 0
+    assert np.abs(full).max() == 0.0
+    assert np.abs(db.cpu().numpy()[Cout:]).max() == 0.0 if cpad > Cout else True
+
+
+DEC_CASES = [(2, 14, 14, 54, 36, 36, True), (3, 15, 11, 24, 16, 16, True), (2, 28, 28, 36, 24, 24, False),
+             (1, 112, 112, 16, 10, 2, True), (2, 7, 9, 6, 0, 5, True)]
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,want_skip_grad", DEC_CASES)
+def test_decoder_stage_forward_and_backward(B, H, W, C0, C1, Cout, want_skip_grad):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + C0)
+    Hh, Wh = (H + 1) // 2, (W + 1) // 2
+    prev_pre = torch.randn(B, Hh, Wh, C0, generator=g)
+    skip = torch.randn(B, H, W, C1, generator=g) if C1 else None
+    k = torch.randn(3, 3, C0 + C1, Cout, generator=g) * 0.2
+    b = torch.randn(Cout, generator=g) * 0.1
+    G = torch.randn(B, H, W, Cout, generator=g)       # gradient w.r.t. the conv pre-activation
+
+    pr = prev_pre.clone().requires_grad_(True)
+    kr = k.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    sr = skip.clone().requires_grad_(True) if C1 else None
+    d_prev = F.leaky_relu(pr, SLOPE)
+    u = up_ref(d_prev, (H, W))
+    if C1:
+        u = torch.cat([u, sr], dim=3)
+    z = conv_ref(u, kr, br)
+    act = F.leaky_relu(z, SLOPE)
+    (z * G).sum().backward()
+
+    c0p, c1p, coutp = layout.planes(C0), layout.planes(C1), layout.planes(Cout)
+    cpad = layout.round_up(Cout, 16)
+    splits = [C0] + ([C1] if C1 else [])
+    wp = dev(layout.pack_conv(k.numpy(), splits, cpad))
+    bias = torch.zeros(cpad, device="cuda")
+    bias[:Cout] = b.cuda()
+    d_prev_dev = p4(d_prev.detach().numpy())
+    skip_dev = p4(skip.numpy()) if C1 else None
+    out_full = torch.zeros(B, coutp, H, W, 4, device="cuda")
+    check(lib.dincae_conv3x3_fwd(ptr(d_prev_dev), c0p, 1, ptr(skip_dev), c1p, ptr(wp), ptr(bias),
+                                 cpad, B, H, W, coutp, SLOPE, ptr(out_full), None, None, stream()))
+    torch.cuda.synchronize()
+    assert rel_err(from_p4(out_full, Cout), act.detach().numpy()) < TOL
+
+    Gd = p4(G.numpy())
+    g_prev = torch.zeros(B, c0p, Hh, Wh, 4, device="cuda")
+    use_hi = bool(C1) and want_skip_grad
+    dx_hi = torch.zeros(B, max(c1p, 1), H, W, 4, device="cuda")
+    check(lib.dincae_conv3x3_dgrad(ptr(Gd), None, None, SLOPE, coutp, ptr(wp), c0p + c1p, cpad,
+                                   B, H, W, c0p, ptr(d_prev_dev), SLOPE, ptr(g_prev),
+                                   c1p if use_hi else 0, ptr(dx_hi) if use_hi else None, None,
+                                   stream()))
+    ws_bytes = lib.dincae_conv3x3_wgrad_workspace(c0p, c1p, cpad, B, H, W)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((9, c0p + c1p, cpad, 4), 7.0, device="cuda")
+    db = torch.full((cpad,), 7.0, device="cuda")
+    check(lib.dincae_conv3x3_wgrad(ptr(d_prev_dev), c0p, 1, ptr(skip_dev), c1p, ptr(Gd), None, None,
+                                   SLOPE, coutp, cpad, B, H, W, ptr(dw), ptr(db), ptr(ws), ws_bytes,
+                                   stream()))
+    torch.cuda.synchronize()
+    assert rel_err(from_p4(g_prev, C0), pr.grad.numpy()) < TOL
+    if use_hi:
+        assert rel_err(from_p4(dx_hi, C1), sr.grad.numpy()) < TOL
+    assert rel_err(layout.unpack_conv(dw.cpu().numpy(), splits, Cout), kr.grad.numpy()) < TOL
+    assert rel_err(db.cpu().numpy()[:Cout], br.grad.numpy()) < TOL
+
+
+def test_relu_bottleneck_slope_and_no_prev_act():
+    """prev_slope = 0 (dense ReLU below the first decoder conv) and prev_act = NULL."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    B, H, W, C0, Cout = 2, 6, 10, 8, 4
+    Hh, Wh = 3, 5
+    pre = torch.randn(B, Hh, Wh, C0, generator=g)
+    k = torch.randn(3, 3, C0, Cout, generator=g)
+    G = torch.randn(B, H, W, Cout, generator=g)
+    pr = pre.clone().requires_grad_(True)
+    act = F.relu(pr)
+    (conv_ref(up_ref(act, (H, W)), k) * G).sum().backward()
+    ar = act.detach().clone().requires_grad_(True)
+    (conv_ref(up_ref(ar, (H, W)), k) * G).sum().backward()
+    cpad = 16
+    wp = dev(layout.pack_conv(k.numpy(), [C0], cpad))
+    act_dev = p4(act.detach().numpy())
+    Gd = p4(G.numpy())
+    for prev, slope, want in ((act_dev, 0.0, pr.grad), (None, 1.0, ar.grad)):
+        g_prev = torch.zeros(B, 2, Hh, Wh, 4, device="cuda")
+        check(lib.dincae_conv3x3_dgrad(ptr(Gd), None, None, SLOPE, 1, ptr(wp), 2, cpad, B, H, W,
+                                       2, ptr(prev), slope, ptr(g_prev), 0, None, None, stream()))
+        torch.cuda.synchronize()
+        assert rel_err(from_p4(g_prev, C0), want.numpy()) < TOL
+
+
+def test_invalid_arguments_are_rejected():
+    lib = _lib.load()
+    x = torch.zeros(16, device="cuda")
+    assert lib.dincae_conv3x3_fwd(None, 1, 0, None, 0, ptr(x), ptr(x), 16, 1, 2, 2, 1, 0.2,
+                                  ptr(x), None, None, stream()) == -1
+    assert lib.dincae_conv3x3_fwd(ptr(x), 1, 0, None, 0, ptr(x), ptr(x), 16, 1, 2, 2, 1, 0.2,
+                                  None, None, None, stream()) == -1
+    assert lib.dincae_conv3x3_fwd(ptr(x), 1, 0, None, 0, ptr(x), ptr(x), 16, 1, 2, 2, 5, 0.2,
+                                  ptr(x), None, None, stream()) == -1
