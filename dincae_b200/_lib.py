@@ -20,6 +20,7 @@ SIGNATURES = {
     "dincae_version": (c_char_p, []),
     "dincae_error_string": (c_char_p, [c_int]),
     "dincae_last_cuda_error": (c_int, []),
+    "dincae_launch_count": (ctypes.c_longlong, [c_int]),
     "dincae_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "dincae_prepare_cube": (c_int, [vp, vp, c_int, c_int, c_int, c_double, c_int, vp, vp, vp, vp]),
     "dincae_build_batch": (c_int, [vp, vp, vp, vp, vp, vp, vp, POINTER(c_double), POINTER(c_double),

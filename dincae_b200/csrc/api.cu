@@ -3,6 +3,7 @@
 
 namespace dincae {
 int g_last_cuda_error = 0;
+long long g_launch_count = 0;
 }
 
 extern "C" const char* dincae_version(void) { return "dincae_b200 0.1.0 (sm_100a)"; }
@@ -19,6 +20,12 @@ extern "C" const char* dincae_error_string(int code) {
 }
 
 extern "C" int dincae_last_cuda_error(void) { return dincae::g_last_cuda_error; }
+
+extern "C" long long dincae_launch_count(int reset) {
+  const long long n = dincae::g_launch_count;
+  if (reset) dincae::g_launch_count = 0;
+  return n;
+}
 
 extern "C" int dincae_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

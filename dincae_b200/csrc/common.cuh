@@ -7,8 +7,10 @@
 namespace dincae {
 
 extern int g_last_cuda_error;
+extern long long g_launch_count;     // diagnostics only: kernels enqueued through this library
 
 inline int check_launch() {
+  ++g_launch_count;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;

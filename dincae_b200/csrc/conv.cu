@@ -129,13 +129,13 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       float v[4];
+      const bool inb = (y < P.H) && (xb + px < P.W);
 #pragma unroll
       for (int co = 0; co < 4; ++co) {
         float z = acc[px][co] + f4_get(bias4, co);
-        if (z > 0.f) bits |= 1u << (4 * px + co);
+        if (z > 0.f && inb) bits |= 1u << (4 * px + co);
         v[co] = z > 0.f ? z : P.slope * z;
       }
-      const bool inb = (y < P.H) && (xb + px < P.W);
       a[px] = inb ? make_float4(v[0], v[1], v[2], v[3]) : f4_zero();
       if (inb && P.out_full)
         P.out_full[((size_t)(b * P.out_planes + op) * P.H + y) * P.W + xb + px] = a[px];

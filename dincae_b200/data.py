@@ -36,42 +36,13 @@ class DeviceCube:
 
         self.anom = torch.empty(nd, T, H, W, dtype=torch.float32, device=dev)
         self.missing = torch.empty(nd, T, H, W, dtype=torch.uint8, device=dev)
-        mean_dev = torch.empty(H, W, dtype=torch.float64, device=dev)
-        never_dev = torch.empty(H, W, dtype=torch.uint8, device=dev)
+        self._raw_dev = torch.empty(T, H, W, dtype=torch.float32, device=dev)
+        self._mean_dev = torch.empty(H, W, dtype=torch.float64, device=dev)
+        self._never_dev = torch.empty(H, W, dtype=torch.uint8, device=dev)
+        self._obs_var = [float(s) ** 2 for s in obs_err_std]
         self.meandata = []
         self.cloud_missing = None
-        for i in range(nd):
-            field = np.ma.asarray(data_full[i])
-            if field.shape != (T, H, W):
-                raise ValueError("shape are not coherent")     # :171-172
-            nomask = field.mask is np.ma.nomask
-            miss = np.ma.getmaskarray(field)
-            if missing is not None and not np.array_equal(np.asarray(missing[i], dtype=bool), miss):
-                # the reference lays `missing` (not data.mask) over the frame as added clouds
-                if self.cloud_missing is None:
-                    self.cloud_missing = self.missing.clone()
-                    for k in range(i):
-                        self.cloud_missing[k].copy_(self.missing[k])
-                self.cloud_missing[i].copy_(
-                    torch.from_numpy(np.ascontiguousarray(missing[i], dtype=bool)).to(torch.uint8))
-            elif self.cloud_missing is not None:
-                self.cloud_missing[i].copy_(
-                    torch.from_numpy(np.ascontiguousarray(miss)).to(torch.uint8))
-            raw = torch.from_numpy(np.ascontiguousarray(np.ma.getdata(field), dtype=np.float32))
-            raw_dev = raw.pin_memory().to(dev, non_blocking=True)
-            self.missing[i].copy_(torch.from_numpy(np.ascontiguousarray(miss)).to(torch.uint8),
-                                  non_blocking=True)
-            check(self.lib.dincae_prepare_cube(
-                ptr(raw_dev), ptr(self.missing[i]), T, H, W, float(obs_err_std[i]) ** 2,
-                int(nomask), ptr(self.anom[i]), ptr(mean_dev), ptr(never_dev), stream_ptr()),
-                "prepare_cube")
-            mean = mean_dev.cpu().numpy().reshape(1, H, W)
-            never = never_dev.cpu().numpy().astype(bool).reshape(1, H, W)
-            if nomask:
-                self.meandata.append(np.ma.asarray(mean.astype(np.float32)))
-            else:
-                self.meandata.append(np.ma.masked_array(mean, never))
-            del raw_dev
+        self.upload(data_full, missing)
 
         lon = np.asarray(lon, dtype=np.float64)
         lat = np.asarray(lat, dtype=np.float64)
@@ -83,6 +54,47 @@ class DeviceCube:
         self.doy_sin = f32(np.sin(2 * np.pi * doy / 365.25))
         self._inv_var_c = _lib.doubles(self.inv_var)
         self._jitter_cache = {}
+
+    def upload(self, data_full, missing=None, fetch_mean=True):
+        """(Re)load the cube from host arrays into the SAME device buffers (pointers captured
+        in CUDA graphs stay valid) and run the temporal-mean pre-pass on the device."""
+        nd, T, H, W = self.ndata, self.T, self.H, self.W
+        self.meandata = []
+        for i in range(nd):
+            field = np.ma.asarray(data_full[i])
+            if field.shape != (T, H, W):
+                raise ValueError("shape are not coherent")     # :171-172
+            nomask = field.mask is np.ma.nomask
+            miss = np.ma.getmaskarray(field)
+            if missing is not None and not np.array_equal(np.asarray(missing[i], dtype=bool), miss):
+                # the reference lays `missing` (not data.mask) over the frame as added clouds
+                if self.cloud_missing is None:
+                    self.cloud_missing = torch.empty_like(self.missing)
+                    for k in range(i):
+                        self.cloud_missing[k].copy_(self.missing[k])
+                self.cloud_missing[i].copy_(
+                    torch.from_numpy(np.ascontiguousarray(missing[i], dtype=bool).view(np.uint8)))
+            elif self.cloud_missing is not None:
+                self.cloud_missing[i].copy_(torch.from_numpy(np.ascontiguousarray(miss).view(np.uint8)))
+            # host -> device: straight from the caller's memory when it is already pinned
+            # float32 / bool storage, through one pinned staging copy otherwise
+            raw = torch.from_numpy(np.ascontiguousarray(np.ma.getdata(field), dtype=np.float32))
+            if not raw.is_pinned():
+                raw = raw.pin_memory()
+            self._raw_dev.copy_(raw, non_blocking=True)
+            mk = torch.from_numpy(np.ascontiguousarray(miss).view(np.uint8))
+            self.missing[i].copy_(mk, non_blocking=True)
+            check(self.lib.dincae_prepare_cube(
+                ptr(self._raw_dev), ptr(self.missing[i]), T, H, W, self._obs_var[i],
+                int(nomask), ptr(self.anom[i]), ptr(self._mean_dev), ptr(self._never_dev),
+                stream_ptr()), "prepare_cube")
+            if fetch_mean:
+                mean = self._mean_dev.cpu().numpy().reshape(1, H, W)
+                never = self._never_dev.cpu().numpy().astype(bool).reshape(1, H, W)
+                if nomask:
+                    self.meandata.append(np.ma.asarray(mean.astype(np.float32)))
+                else:
+                    self.meandata.append(np.ma.masked_array(mean, never))
 
     def nbytes(self):
         return self.anom.numel() * 4 + self.missing.numel()

@@ -234,6 +234,17 @@ class Network:
         self.workspace = torch.zeros(max(ws + [256]), dtype=torch.uint8, device=dev)
         self._ent = {e["name"]: e for e in P.entries}
         self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
+        self.tracer = None       # optional callable(label, fn, args, alg_bytes, alg_flops)
+
+    def _call(self, label, fname, args, alg_bytes=0, alg_flops=0):
+        """Enqueue one C-ABI call.  ``alg_bytes`` / ``alg_flops`` are the ALGORITHMIC traffic
+        and work of the call (fp32, logical channel counts, every tensor touched once; see
+        DESIGN.md) -- used by bench.py's roofline report through ``self.tracer``."""
+        fn = getattr(self.lib, fname)
+        if self.tracer is None:
+            check(fn(*args), label)
+        else:
+            self.tracer(label, fn, args, alg_bytes, alg_flops)
 
     # ---- parameters -----------------------------------------------------------------------
     def _conv_res(self, e):
@@ -276,32 +287,41 @@ class Network:
         for l in range(1, P.L + 1):
             h, w = P.sizes[l - 1]
             e = self._ent[self._enc_name(l) + "/kernel"]
-            check(lib.dincae_conv3x3_fwd(
+            ci, co = P.enc_c[l - 1], P.enc_c[l]
+            hh, wh = P.sizes[l]
+            nb = 4 * B * (h * w * ci + hh * wh * co) + 36 * ci * co + (B * h * w * co // 8 if save_signs else 0)
+            self._call("conv3x3_fwd(enc %d)" % l, "dincae_conv3x3_fwd", (
                 ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
                 ptr(self._w(e["name"])), ptr(self._w(self._enc_name(l) + "/bias")), e["cout_pad"],
                 B, h, w, P.ep[l], NEG_SLOPE, None, ptr(self.X[l]),
-                ptr(self.S[l]) if save_signs else None, st), "conv3x3_fwd(enc %d)" % l)
+                ptr(self.S[l]) if save_signs else None, st), nb, 18 * ci * co * B * h * w)
         for i in range(len(P.dense_units)):
             name = "dense" if i == 0 else "dense_%d" % i
-            check(lib.dincae_dense_fwd(
+            kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._call("dense_fwd(%d)" % i, "dincae_dense_fwd", (
                 ptr(self.F[i]), ptr(self._w(name + "/kernel")), ptr(self._w(name + "/bias")),
                 B, P.dense_pad[i], P.dense_pad[i + 1], 1, ptr(self.F[i + 1]),
-                ptr(self.workspace), self.workspace.numel(), st), "dense_fwd(%d)" % i)
+                ptr(self.workspace), self.workspace.numel(), st),
+                4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
         for l in range(1, P.L + 1):
             up, sk, r = P.dec_sources(l)
             h, w = P.sizes[r]
             e = self._ent[self._dec_name(l) + "/kernel"]
-            check(lib.dincae_conv3x3_fwd(
-                ptr(self.D[l - 1]), P.dp[l - 1] if l > 1 else P.ep[P.L], 1,
+            hh, wh = P.sizes[r + 1]
+            co = P.dec_c[l]
+            nb = 4 * B * (hh * wh * up + h * w * (sk + co)) + 36 * (up + sk) * co
+            self._call("conv3x3_fwd(dec %d)" % l, "dincae_conv3x3_fwd", (
+                ptr(self.D[l - 1]), P.dp[l - 1], 1,
                 ptr(self.X[r]) if sk else None, P.ep[r] if sk else 0,
                 ptr(self._w(e["name"])), ptr(self._w(self._dec_name(l) + "/bias")), e["cout_pad"],
                 B, h, w, P.dp[l], NEG_SLOPE, ptr(self.D[l]), None, None, st),
-                "conv3x3_fwd(dec %d)" % l)
+                nb, 18 * (up + sk) * co * B * h * w)
 
     def head_recon(self, B):
         P = self.plan
-        check(self.lib.dincae_head_recon(ptr(self.D[P.L]), B, P.H, P.W, ptr(self.m_rec),
-                                         ptr(self.s2_rec), stream_ptr()), "head_recon")
+        self._call("head_recon", "dincae_head_recon", (
+            ptr(self.D[P.L]), B, P.H, P.W, ptr(self.m_rec), ptr(self.s2_rec), stream_ptr()),
+            16 * B * P.H * P.W, 0)
 
     # ---- loss + backward --------------------------------------------------------------------
     def loss_backward(self, B, truth_uncertain=False, normalise=True):
@@ -309,75 +329,87 @@ class Network:
         P, lib, st = self.plan, self.lib, stream_ptr()
         L = P.L
         wsp, wsn = ptr(self.workspace), self.workspace.numel()
-        check(lib.dincae_head_loss(
+        self._call("head_loss", "dincae_head_loss", (
             ptr(self.D[L]), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
             ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self.loss_sums),
-            ptr(self.loss_out), wsp, wsn, st), "head_loss")
+            ptr(self.loss_out), wsp, wsn, st), 24 * B * P.H * P.W, 0)
         has_dense = len(P.dense_units) > 0
         for l in range(L, 0, -1):
             up, sk, r = P.dec_sources(l)
             h, w = P.sizes[r]
             name = self._dec_name(l)
             e = self._ent[name + "/kernel"]
-            c0p = P.dp[l - 1] if l > 1 else P.ep[L]
+            c0p = P.dp[l - 1]
             c1p = P.ep[r] if sk else 0
-            check(lib.dincae_conv3x3_wgrad(
+            hh, wh = P.sizes[r + 1]
+            co = P.dec_c[l]
+            nb = 4 * B * (hh * wh * up + h * w * (sk + co)) + 36 * (up + sk) * co
+            self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.D[l - 1]), c0p, 1, ptr(self.X[r]) if sk else None, c1p,
                 ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l], e["cout_pad"], B, h, w,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                wsp, wsn, st), "conv3x3_wgrad(dec %d)" % l)
+                wsp, wsn, st), nb, 18 * (up + sk) * co * B * h * w)
             prev_slope = NEG_SLOPE if l > 1 else (0.0 if has_dense else 1.0)
             want_skip = bool(sk) and r >= 1
-            check(lib.dincae_conv3x3_dgrad(
+            cin_eff = up + (sk if want_skip else 0)
+            nb = 4 * B * (h * w * co + 2 * hh * wh * up + (h * w * sk if want_skip else 0)) + 36 * cin_eff * co
+            self._call("conv3x3_dgrad(dec %d)" % l, "dincae_conv3x3_dgrad", (
                 ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l],
                 ptr(self._w(name + "/kernel")), e["cinp"], e["cout_pad"], B, h, w,
                 c0p, ptr(self.D[l - 1]), prev_slope, ptr(self.GD[l - 1]),
                 c1p if want_skip else 0, ptr(self.dXskip[r]) if want_skip else None, None, st),
-                "conv3x3_dgrad(dec %d)" % l)
+                nb, 18 * cin_eff * co * B * h * w)
         nd = len(P.dense_units)
         for i in range(nd - 1, -1, -1):
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
-            check(lib.dincae_dense_bwd_weight(
+            kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
                 ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                st), "dense_bwd_weight(%d)" % i)
+                st), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn)
             dst = self.dZ[i] if i > 0 else self.dX[L].view(self.Bmax, -1)
-            check(lib.dincae_dense_bwd_data(
+            self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
                 ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
                 ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
-                "dense_bwd_data(%d)" % i)
+                4 * (B * nn + kk * nn + B * kk), 2 * B * kk * nn)
         top_grad = self.dX[L] if has_dense else self.GD[0]
         for l in range(L, 0, -1):
             h, w = P.sizes[l - 1]
             name = self._enc_name(l)
             e = self._ent[name + "/kernel"]
             gpool = top_grad if l == L else self.dX[l]
-            check(lib.dincae_conv3x3_wgrad(
+            ci, co = P.enc_c[l - 1], P.enc_c[l]
+            hh, wh = P.sizes[l]
+            nb = 4 * B * (h * w * ci + hh * wh * co) + B * h * w * co // 8 + 36 * ci * co
+            self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
                 None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l], e["cout_pad"], B, h, w,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                wsp, wsn, st), "conv3x3_wgrad(enc %d)" % l)
+                wsp, wsn, st), nb, 18 * ci * co * B * h * w)
             if l > 1:
-                check(lib.dincae_conv3x3_dgrad(
+                has_add = self.dXskip[l - 1] is not None
+                nb = 4 * B * (hh * wh * co + h * w * ci * (2 if has_add else 1)) + B * h * w * co // 8 + 36 * ci * co
+                self._call("conv3x3_dgrad(enc %d)" % l, "dincae_conv3x3_dgrad", (
                     None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l],
                     ptr(self._w(name + "/kernel")), e["cinp"], e["cout_pad"], B, h, w,
                     0, None, 1.0, None,
                     P.ep[l - 1], ptr(self.dX[l - 1]),
-                    ptr(self.dXskip[l - 1]) if self.dXskip[l - 1] is not None else None, st),
-                    "conv3x3_dgrad(enc %d)" % l)
+                    ptr(self.dXskip[l - 1]) if has_add else None, st),
+                    nb, 18 * ci * co * B * h * w)
 
     def l2_value(self):
         """0.5 * sum of squares of all kernels -> self.l2_out (device)."""
-        check(self.lib.dincae_l2_half_sumsq(ptr(self.params), self.plan.n_decay, ptr(self.l2_out),
-                                            ptr(self.workspace), self.workspace.numel(),
-                                            stream_ptr()), "l2_half_sumsq")
+        self._call("l2_half_sumsq", "dincae_l2_half_sumsq", (
+            ptr(self.params), self.plan.n_decay, ptr(self.l2_out), ptr(self.workspace),
+            self.workspace.numel(), stream_ptr()), 4 * self.plan.n_params_tf, 0)
 
     def adam_step(self, clip_norm=5.0, l2_beta=0.0, beta1=0.9, beta2=0.999, eps=1e-8,
                   grad_scale=1.0, denom=None):
         """clip_by_global_norm + Adam on self.grads; learning rate read from self.lr."""
-        check(self.lib.dincae_adam_step(
+        self._call("adam_step", "dincae_adam_step", (
             ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
             self.plan.n_params_flat, self.plan.n_decay, l2_beta, clip_norm, ptr(self.lr),
             beta1, beta2, eps, grad_scale, ptr(denom), ptr(self.adam_state),
-            ptr(self.workspace), self.workspace.numel(), stream_ptr()), "adam_step")
+            ptr(self.workspace), self.workspace.numel(), stream_ptr()),
+            28 * self.plan.n_params_tf, 0)

@@ -116,6 +116,10 @@ class Trainer:
     def train_step(self, frame_idx, cloud_idx, seq):
         """Enqueue one step for this rank's B frames; the loss is fetched lazily."""
         self.upload_indices(frame_idx, cloud_idx, seq)
+        self.run_step()
+
+    def run_step(self):
+        """One step on the indices already in ``self.idx_dev``."""
         if self.dist is None:
             self._run("step", lambda: (self._enqueue_fwd_bwd(), self._enqueue_update()))
         else:

@@ -45,6 +45,9 @@ extern "C" {
 const char* dincae_version(void);
 const char* dincae_error_string(int code);
 int dincae_last_cuda_error(void);
+/* Number of kernels this library has enqueued since the last reset (diagnostics for
+ * bench.py's gpu_launches; the only process-global state besides the last CUDA error). */
+long long dincae_launch_count(int reset);
 /* sm_count, compute capability of the current device. */
 int dincae_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

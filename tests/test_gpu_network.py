@@ -64,7 +64,9 @@ def test_param_layout_matches_tf_variables(case):
 def test_forward_loss_gradients(case, uncertain, beta):
     c, arch, plan, params, xin, xtrue = make(case, seed=1)
     B = c["B"]
-    cost, rms, n, grads, xrec, keep = M.loss_and_grads(arch, params, xin, xtrue, uncertain, beta)
+    # float64 oracle: the arbiter when two float32 evaluations (CPU / GPU) disagree
+    cost, rms, n, grads, xrec, keep = M.loss_and_grads(
+        arch, [p.double() for p in params], xin.double(), xtrue.double(), uncertain, beta)
     net = Network(plan, B, train=True)
     net.set_params_tf([p.numpy() for p in params])
     load_inputs(net, xin, xtrue)
