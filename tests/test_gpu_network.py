@@ -67,6 +67,7 @@ def test_forward_loss_gradients(case, uncertain, beta):
     # float64 oracle: the arbiter when two float32 evaluations (CPU / GPU) disagree
     cost, rms, n, grads, xrec, keep = M.loss_and_grads(
         arch, [p.double() for p in params], xin.double(), xtrue.double(), uncertain, beta)
+    grads32 = M.loss_and_grads(arch, params, xin, xtrue, uncertain, beta)[3]
     net = Network(plan, B, train=True)
     net.set_params_tf([p.numpy() for p in params])
     load_inputs(net, xin, xtrue)
@@ -85,10 +86,15 @@ def test_forward_loss_gradients(case, uncertain, beta):
     assert abs(net.loss_out[1].item() - rms.item()) < 5e-5 * max(1.0, abs(rms.item()))
     got_grads = net.get_grads_tf()
     names = [nm for nm, _ in arch.param_shapes()]
-    for nm, gg, gw, p in zip(names, got_grads, grads, params):
+    for nm, gg, gw, g32, p in zip(names, got_grads, grads, grads32, params):
         want = gw.numpy() - (beta * p.numpy() if "bias" not in nm else 0.0)   # L2 term joins in Adam
         scale = max(np.abs(want).max(), 1e-6)
-        assert np.abs(gg - want).max() / scale < 2e-4, nm
+        # fp32 kernels vs fp64 oracle.  A pre-activation that rounds to the other side of zero
+        # flips a leaky-ReLU slope (1 <-> 0.2): a discrete O(1e-4..1e-3) effect on the first
+        # layer's gradient that the fp32 CPU evaluation shows as well, so the bound is the
+        # larger of 1e-4 and 3x the fp32-CPU error against the same fp64 arbiter.
+        cpu_err = float((g32.double() - gw).abs().max()) / scale
+        assert np.abs(gg - want).max() / scale < max(1e-4, 3 * cpu_err), nm
     # head for reconstruction
     net.head_recon(B)
     torch.cuda.synchronize()
