@@ -6,32 +6,13 @@
 // intermediate tensors of the TF graph (DINCAE/__init__.py:442-452, 496-513) ever exists
 // in HBM.
 #include "common.cuh"
+#include "conv_params.cuh"
 
 namespace dincae {
 
 constexpr int CPB = 4;   // logical output planes per block (one per 64 threads)
 constexpr int CK = 4;    // logical input planes staged in shared memory per step
 
-struct ConvParams {
-  ConvSrc src;
-  const float* w;        // WP [9][w_cinp][cout_pad][4]
-  const float* bias;     // [cout_pad] (forward) or null
-  int w_cinp, cout_pad;
-  int B, H, W;
-  int out_planes;        // logical output planes to compute
-  float slope;
-  // forward outputs
-  float4* out_full;
-  float4* out_pool;
-  uint16_t* out_sign;
-  // data-gradient outputs
-  int c_lo, c_hi;
-  const float4* prev_act;
-  float prev_slope;
-  float4* g_prev;
-  float4* dx_hi;
-  const float4* dx_add;
-};
 
 // MODE 0: forward.  MODE 1: data gradient (weights read transposed, taps mirrored).
 // Block = 256 threads = 64 pixel-quads (4 consecutive x each) x CPB output planes; thread
@@ -417,6 +398,18 @@ static void wgrad_plan(int cinp, int gp, int B, int H, int W, int& cib, int& cob
 
 using namespace dincae;
 
+namespace dincae {
+int g_conv_backend = 1;
+}
+
+extern "C" int dincae_set_conv_backend(int backend) {
+  if (backend != 0 && backend != 1) return DINCAE_EINVAL;
+  g_conv_backend = backend;
+  return DINCAE_OK;
+}
+
+extern "C" int dincae_get_conv_backend(void) { return g_conv_backend; }
+
 extern "C" int dincae_conv3x3_fwd(const float* src0, int c0p, int src0_half, const float* src1,
                                   int c1p, const float* wpack, const float* bias, int cout_pad,
                                   int B, int H, int W, int coutp, float neg_slope,
@@ -432,6 +425,10 @@ extern "C" int dincae_conv3x3_fwd(const float* src0, int c0p, int src0_half, con
   P.out_full = reinterpret_cast<float4*>(out_full);
   P.out_pool = reinterpret_cast<float4*>(out_pool);
   P.out_sign = out_sign;
+  if (g_conv_backend == 1) {
+    const int rc = launch_conv_mma(0, P, out_pool ? coutp : 0, (cudaStream_t)stream);
+    if (rc <= 0) return rc;          // 1 = shape not taken by the tensor-core path
+  }
   return launch_conv<0>(P, (cudaStream_t)stream);
 }
 
@@ -454,6 +451,10 @@ extern "C" int dincae_conv3x3_dgrad(const float* g_full, const float* g_pool, co
   P.g_prev = reinterpret_cast<float4*>(g_prev);
   P.dx_hi = reinterpret_cast<float4*>(dx_hi);
   P.dx_add = reinterpret_cast<const float4*>(dx_add);
+  if (g_conv_backend == 1) {
+    rc = launch_conv_mma(1, P, c_lo, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   return launch_conv<1>(P, (cudaStream_t)stream);
 }
 

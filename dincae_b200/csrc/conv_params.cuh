@@ -1,0 +1,36 @@
+// Parameter block shared by the FFMA and the tcgen05 convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dincae {
+
+struct ConvParams {
+  ConvSrc src;
+  const float* w;        // WP [9][w_cinp][cout_pad][4]
+  const float* bias;     // [cout_pad] (forward) or null
+  int w_cinp, cout_pad;
+  int B, H, W;
+  int out_planes;        // logical output planes to compute
+  float slope;
+  // forward outputs
+  float4* out_full;
+  float4* out_pool;
+  uint16_t* out_sign;
+  // data-gradient outputs
+  int c_lo, c_hi;
+  const float4* prev_act;
+  float prev_slope;
+  float4* g_prev;
+  float4* dx_hi;
+  const float4* dx_add;
+};
+
+extern int g_conv_backend;      // 0: fp32 FFMA kernels, 1: tcgen05 TF32 implicit GEMM
+
+// Tensor-core path (conv_mma.cu).  mode 0 forward, 1 data gradient.  Returns 0 on success,
+// a negative DINCAE_E* code, or 1 when the shape does not fit and the caller should use
+// the FFMA kernel.  stage_planes: planes that go through the 2x2 reduction (pool / upsample
+// gradient).
+int launch_conv_mma(int mode, const ConvParams& P, int stage_planes, cudaStream_t st);
+
+}  // namespace dincae

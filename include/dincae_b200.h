@@ -89,6 +89,13 @@ int dincae_build_batch(const float* anom, const uint8_t* missing,
 
 /* ---- 3x3 convolutions -------------------------------------------------------------- */
 
+/* Which kernels dincae_conv3x3_fwd / dincae_conv3x3_dgrad launch: 1 (default) = tcgen05
+ * kind::tf32 implicit GEMM with TMEM accumulators (operands rounded to TF32, fp32 accumulate),
+ * 0 = fp32 FFMA kernels (bit-for-bit fp32 arithmetic; also taken automatically for shapes the
+ * tensor-core path does not cover).  Process-wide setting. */
+int dincae_set_conv_backend(int backend);
+int dincae_get_conv_backend(void);
+
 /* tf.layers.conv2d(3x3, SAME) + leaky_relu [+ average_pooling2d(2,2,SAME)],
  * DINCAE/__init__.py:442-452 (encoder) and :496-513 (decoder: resize + concat + conv).
  * Input = concat(src0 [c0p planes; half-res if src0_half], src1 [c1p planes, may be NULL]).

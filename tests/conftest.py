@@ -24,3 +24,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=[0, 1], ids=["ffma_fp32", "tcgen05_tf32"])
+def backend(request):
+    """Run a GPU test under both convolution back ends (include/dincae_b200.h:
+    dincae_set_conv_backend).  Yields the back-end id; restores the default afterwards."""
+    from dincae_b200 import _lib
+    lib = _lib.load()
+    assert lib.dincae_set_conv_backend(request.param) == 0
+    yield request.param
+    lib.dincae_set_conv_backend(1)

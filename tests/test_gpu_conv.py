@@ -11,8 +11,10 @@ from dincae_b200._lib import check, ptr
 from tests.util import dev, from_p4, p4, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-5
 SLOPE = 0.2
+# fp32 FFMA kernels: rounding-level agreement.  tcgen05 kind::tf32: operands rounded to 10
+# mantissa bits (2^-11 relative each), fp32 accumulation -> 2e-3 of the tensor's max.
+TOLS = {0: 2e-5, 1: 2e-3}
 
 
 def nchw(x):
@@ -44,8 +46,9 @@ ENC_CASES = [(2, 12, 20, 10, 16), (3, 15, 11, 16, 24), (2, 7, 7, 36, 54), (1, 11
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", ENC_CASES)
-def test_encoder_stage_forward_and_backward(B, H, W, Cin, Cout):
+def test_encoder_stage_forward_and_backward(B, H, W, Cin, Cout, backend):
     lib = _lib.load()
+    TOL = TOLS[backend]
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
     x = torch.randn(B, H, W, Cin, generator=g)
     k = torch.randn(3, 3, Cin, Cout, generator=g) * 0.2
@@ -83,10 +86,13 @@ def test_encoder_stage_forward_and_backward(B, H, W, Cin, Cout):
     want_sign = layout.sign_mask(z.detach().numpy())
     got_sign = out_sign.cpu().numpy().view(np.uint16)
     diff = want_sign ^ got_sign
-    zmin = np.abs(z.detach().numpy())
-    assert np.count_nonzero(diff) <= np.count_nonzero(zmin < 1e-5)
+    zabs = np.abs(z.detach().numpy())
+    nflip = sum(bin(int(v)).count("1") for v in diff.reshape(-1) if v)
+    assert nflip <= np.count_nonzero(zabs < TOL * zabs.max())
 
-    # backward through pool + leaky relu (sign mask from the kernel itself)
+    # backward through pool + leaky relu; the mask of the REFERENCE pre-activation is used so
+    # that a rounding-level sign flip of the forward does not leak into this comparison
+    out_sign = dev(want_sign.view(np.int16))
     gp = p4(gpool.numpy())
     dx = torch.zeros(B, cinp, H, W, 4, device="cuda")
     add = p4(dx_add.numpy())
@@ -115,8 +121,9 @@ DEC_CASES = [(2, 14, 14, 54, 36, 36, True), (3, 15, 11, 24, 16, 16, True), (2, 2
 
 
 @pytest.mark.parametrize("B,H,W,C0,C1,Cout,want_skip_grad", DEC_CASES)
-def test_decoder_stage_forward_and_backward(B, H, W, C0, C1, Cout, want_skip_grad):
+def test_decoder_stage_forward_and_backward(B, H, W, C0, C1, Cout, want_skip_grad, backend):
     lib = _lib.load()
+    TOL = TOLS[backend]
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + C0)
     Hh, Wh = (H + 1) // 2, (W + 1) // 2
     prev_pre = torch.randn(B, Hh, Wh, C0, generator=g)
@@ -174,9 +181,10 @@ def test_decoder_stage_forward_and_backward(B, H, W, C0, C1, Cout, want_skip_gra
     assert rel_err(db.cpu().numpy()[:Cout], br.grad.numpy()) < TOL
 
 
-def test_relu_bottleneck_slope_and_no_prev_act():
+def test_relu_bottleneck_slope_and_no_prev_act(backend):
     """prev_slope = 0 (dense ReLU below the first decoder conv) and prev_act = NULL."""
     lib = _lib.load()
+    TOL = TOLS[backend]
     g = torch.Generator().manual_seed(3)
     B, H, W, C0, Cout = 2, 6, 10, 8, 4
     Hh, Wh = 3, 5

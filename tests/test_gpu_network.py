@@ -59,9 +59,15 @@ def test_param_layout_matches_tf_variables(case):
         assert np.array_equal(a, b.numpy())
 
 
+# tolerance multipliers of the tcgen05 kind::tf32 back end relative to the fp32 one
+# (operands carry 10 mantissa bits; measured errors are printed by the tests)
+TF32 = {0: 1.0, 1: 100.0}
+
+
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("uncertain,beta", [(False, 0.0), (True, 0.001)])
-def test_forward_loss_gradients(case, uncertain, beta):
+def test_forward_loss_gradients(case, uncertain, beta, backend):
+    k = TF32[backend]
     c, arch, plan, params, xin, xtrue = make(case, seed=1)
     B = c["B"]
     # float64 oracle: the arbiter when two float32 evaluations (CPU / GPU) disagree
@@ -78,12 +84,16 @@ def test_forward_loss_gradients(case, uncertain, beta):
     L = plan.L
     for l in range(1, L + 1):
         got = from_p4(net.X[l][:B], plan.enc_c[l])
-        assert rel_err(got, keep["enc_pool"][l].detach().numpy()) < 2e-5, "enc_pool %d" % l
+        e1 = rel_err(got, keep["enc_pool"][l].detach().numpy())
+        assert e1 < 2e-5 * k, "enc_pool %d" % l
         got = from_p4(net.D[l][:B], plan.dec_c[l])
-        assert rel_err(got, keep["dec"][l].detach().numpy()) < 5e-5, "dec %d" % l
+        e2 = rel_err(got, keep["dec"][l].detach().numpy())
+        assert e2 < 5e-5 * k, "dec %d" % l
+        print("layer %d: enc_pool err %.2e dec err %.2e" % (l, e1, e2))
     got_cost = net.loss_out[0].item() + beta * net.l2_out.item()
-    assert abs(got_cost - cost.item()) < 5e-5 * max(1.0, abs(cost.item()))
-    assert abs(net.loss_out[1].item() - rms.item()) < 5e-5 * max(1.0, abs(rms.item()))
+    print("cost %.7f oracle %.7f" % (got_cost, cost.item()))
+    assert abs(got_cost - cost.item()) < 5e-5 * k * max(1.0, abs(cost.item()))
+    assert abs(net.loss_out[1].item() - rms.item()) < 5e-5 * k * max(1.0, abs(rms.item()))
     got_grads = net.get_grads_tf()
     names = [nm for nm, _ in arch.param_shapes()]
     for nm, gg, gw, g32, p in zip(names, got_grads, grads, grads32, params):
@@ -94,17 +104,28 @@ def test_forward_loss_gradients(case, uncertain, beta):
         # layer's gradient that the fp32 CPU evaluation shows as well, so the bound is the
         # larger of 1e-4 and 3x the fp32-CPU error against the same fp64 arbiter.
         cpu_err = float((g32.double() - gw).abs().max()) / scale
-        assert np.abs(gg - want).max() / scale < max(1e-4, 3 * cpu_err), nm
+        err = np.abs(gg - want).max() / scale
+        l2 = float(np.linalg.norm((gg - want).ravel()) / max(np.linalg.norm(want.ravel()), 1e-30))
+        print("grad %-16s max-norm err %.2e  L2 err %.2e" % (nm, err, l2))
+        if backend == 0:
+            assert err < max(1e-4, 3 * cpu_err), nm
+        else:
+            # TF32 operands perturb every pre-activation by ~3e-4 of its scale; the ones that
+            # land on the other side of zero switch their leaky-ReLU slope, so a weight
+            # gradient (a sum of +-terms over all pixels) moves by ~sqrt(flipped/total).
+            # Bound the relative L2 error of each gradient tensor and its worst entry.
+            assert l2 < 3e-2 and err < 6e-2, nm
     # head for reconstruction
     net.head_recon(B)
     torch.cuda.synchronize()
     m_rec, s2 = M.head(xrec)
-    assert rel_err(net.m_rec[:B].cpu().numpy(), m_rec.numpy()) < 5e-5
-    assert rel_err(net.s2_rec[:B].cpu().numpy(), s2.numpy()) < 5e-5
+    assert rel_err(net.m_rec[:B].cpu().numpy(), m_rec.numpy()) < 5e-5 * k
+    assert rel_err(net.s2_rec[:B].cpu().numpy(), s2.numpy()) < 5e-5 * k
 
 
 @pytest.mark.parametrize("case", ["tiny", "odd", "nodense_partskip"])
-def test_three_adam_steps_match_oracle(case):
+def test_three_adam_steps_match_oracle(case, backend):
+    k = TF32[backend]
     c, arch, plan, params, xin, xtrue = make(case, seed=2)
     B = c["B"]
     beta, uncertain, lr = 0.001, False, 1e-3
@@ -123,17 +144,20 @@ def test_three_adam_steps_match_oracle(case):
         net.l2_value()
         net.adam_step(clip_norm=5.0, l2_beta=beta, denom=net.loss_sums[3:4])
         torch.cuda.synchronize()
-        assert abs(net.adam_state[2].item() - norm.item()) < 2e-4 * norm.item()
+        assert abs(net.adam_state[2].item() - norm.item()) < 2e-4 * k * norm.item()
         got_cost = net.loss_out[0].item() + beta * net.l2_out.item()
-        assert abs(got_cost - cost.item()) < 1e-4 * max(1.0, abs(cost.item()))
+        assert abs(got_cost - cost.item()) < 1e-4 * k * max(1.0, abs(cost.item()))
     for nm, a, b in zip([n_ for n_, _ in arch.param_shapes()], net.get_params_tf(), ps):
-        assert np.abs(a - b.numpy()).max() < 2e-5, nm
+        # Adam normalises the step: |delta| <= lr per step whatever the gradient scale, so a
+        # rounding-level gradient difference moves a weight by a fraction of 3*lr at most
+        assert np.abs(a - b.numpy()).max() < (2e-5 if backend == 0 else 3e-3), nm
     # padded entries of the flat parameter vector never move away from zero
     flat = net.params.cpu().numpy()
     assert np.array_equal(plan.pack(net.get_params_tf()), flat)
 
 
-def test_partial_batch_uses_prefix_of_buffers():
+def test_partial_batch_uses_prefix_of_buffers(backend):
+    k = TF32[backend]
     c, arch, plan, params, xin, xtrue = make("odd", seed=3)
     net = Network(plan, 8, train=False)
     net.set_params_tf([p.numpy() for p in params])
@@ -143,4 +167,4 @@ def test_partial_batch_uses_prefix_of_buffers():
     net.head_recon(B)
     torch.cuda.synchronize()
     m_rec, s2 = M.head(M.forward(arch, params, xin))
-    assert rel_err(net.m_rec[:B].cpu().numpy(), m_rec.numpy()) < 5e-5
+    assert rel_err(net.m_rec[:B].cpu().numpy(), m_rec.numpy()) < 5e-5 * k
