@@ -89,6 +89,7 @@ struct BatchParams {
   int32_t* n_noncloud;
   uint64_t seed;
   int ndata, T, H, W, ntime_win, B, nvar_planes;
+  int round_tf32;          // network inputs rounded to TF32 (tensor-core conv back end)
   float inv_var[DINCAE_MAX_NDATA];
   double jitter[DINCAE_MAX_NDATA];
 };
@@ -173,8 +174,9 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
         }
         lane[k] = v;
       }
-      reinterpret_cast<float4*>(P.xin)[((size_t)(b * P.nvar_planes + plane) * P.H + y) * P.W + x] =
-          make_float4(lane[0], lane[1], lane[2], lane[3]);
+      float4 out = make_float4(lane[0], lane[1], lane[2], lane[3]);
+      if (P.round_tf32) out = to_tf32(out);
+      reinterpret_cast<float4*>(P.xin)[((size_t)(b * P.nvar_planes + plane) * P.H + y) * P.W + x] = out;
     }
     // target: un-perturbed channels 0 and 1 of the current frame (:227)
     {
@@ -239,6 +241,7 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   P.n_noncloud = n_noncloud; P.seed = seed;
   P.ndata = ndata; P.T = T; P.H = H; P.W = W; P.ntime_win = ntime_win; P.B = B;
   P.nvar_planes = nvar_planes;
+  P.round_tf32 = g_conv_backend == 1;
   for (int j = 0; j < DINCAE_MAX_NDATA; ++j) {
     P.inv_var[j] = j < ndata ? (float)inv_var_host[j] : 0.f;
     P.jitter[j] = (j < ndata && jitter_std_host) ? jitter_std_host[j] : 0.0;

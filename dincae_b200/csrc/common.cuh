@@ -59,6 +59,19 @@ __device__ __forceinline__ float f4_get(const float4& a, int i) {
   return i == 0 ? a.x : (i == 1 ? a.y : (i == 2 ? a.z : a.w));
 }
 
+// round-to-nearest (ties away from zero) to the 10-bit TF32 mantissa == cvt.rna.tf32.f32 for
+// finite values; two full-rate integer ops instead of the multi-instruction cvt expansion
+__device__ __forceinline__ float to_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float4 to_tf32(float4 v) {
+  return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+
+// Tensor-core back end selected (dincae_set_conv_backend): every kernel that produces a tensor
+// a convolution reads rounds it to TF32 on store, because tcgen05 would otherwise truncate.
+extern int g_conv_backend;      // 0: fp32 FFMA kernels, 1: tcgen05 TF32 implicit GEMM
+
 // Logical conv input U[b][plane][y][x] (one float4 = 4 channels) assembled on the fly:
 //   mode 0: concat(s0 [p0 planes, optionally stored at half resolution], s1 [p1 planes])
 //   mode 1: gradient of an encoder stage: gpool[y>>1][x>>1] / window_count * lrelu'(sign)

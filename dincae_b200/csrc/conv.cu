@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
       }
       a[px] = inb ? make_float4(v[0], v[1], v[2], v[3]) : f4_zero();
       if (inb && P.out_full)
-        P.out_full[((size_t)(b * P.out_planes + op) * P.H + y) * P.W + xb + px] = a[px];
+        P.out_full[((size_t)(b * P.out_planes + op) * P.H + y) * P.W + xb + px] = P.round_out ? to_tf32(a[px]) : a[px];
     }
     if (P.out_sign && y < P.H && xb < P.W) {
       const int Wq = (P.W + 3) >> 2;
@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
           const int x = xb + 2 * q;
           if (x < P.W) {
             const int cx = (x + 1 < P.W) ? 2 : 1;
+            const float4 pv = f4_scale(h[q], 1.0f / (float)(cx * cy));
             P.out_pool[((size_t)(b * P.out_planes + op) * Hh + (y >> 1)) * Wh + (x >> 1)] =
-                f4_scale(h[q], 1.0f / (float)(cx * cy));
+                P.round_out ? to_tf32(pv) : pv;
           }
         }
       }
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
               g.z *= pa.z > 0.f ? 1.0f : P.prev_slope;
               g.w *= pa.w > 0.f ? 1.0f : P.prev_slope;
             }
-            P.g_prev[at] = g;
+            P.g_prev[at] = P.round_out ? to_tf32(g) : g;
           }
         }
       }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
           const size_t at = ((size_t)(b * P.c_hi + hp) * P.H + y) * P.W + xb + px;
           float4 v = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
           if (P.dx_add) v = f4_add(v, __ldg(&P.dx_add[at]));
-          P.dx_hi[at] = v;
+          P.dx_hi[at] = P.round_out ? to_tf32(v) : v;
         }
       }
     }
@@ -425,8 +426,9 @@ extern "C" int dincae_conv3x3_fwd(const float* src0, int c0p, int src0_half, con
   P.out_full = reinterpret_cast<float4*>(out_full);
   P.out_pool = reinterpret_cast<float4*>(out_pool);
   P.out_sign = out_sign;
+  P.round_out = g_conv_backend == 1;
   if (g_conv_backend == 1) {
-    const int rc = launch_conv_mma(0, P, out_pool ? coutp : 0, (cudaStream_t)stream);
+    const int rc = launch_conv_tc(0, P, (cudaStream_t)stream);
     if (rc <= 0) return rc;          // 1 = shape not taken by the tensor-core path
   }
   return launch_conv<0>(P, (cudaStream_t)stream);
@@ -451,8 +453,9 @@ extern "C" int dincae_conv3x3_dgrad(const float* g_full, const float* g_pool, co
   P.g_prev = reinterpret_cast<float4*>(g_prev);
   P.dx_hi = reinterpret_cast<float4*>(dx_hi);
   P.dx_add = reinterpret_cast<const float4*>(dx_add);
+  P.round_out = g_conv_backend == 1;
   if (g_conv_backend == 1) {
-    rc = launch_conv_mma(1, P, c_lo, (cudaStream_t)stream);
+    rc = launch_conv_tc(1, P, (cudaStream_t)stream);
     if (rc <= 0) return rc;
   }
   return launch_conv<1>(P, (cudaStream_t)stream);

@@ -23,14 +23,13 @@ struct ConvParams {
   float4* g_prev;
   float4* dx_hi;
   const float4* dx_add;
+  int round_out;         // round stored activations / gradients to TF32 (tensor-core back end)
 };
 
-extern int g_conv_backend;      // 0: fp32 FFMA kernels, 1: tcgen05 TF32 implicit GEMM
 
-// Tensor-core path (conv_mma.cu).  mode 0 forward, 1 data gradient.  Returns 0 on success,
+// Tensor-core path (conv_tc.cu).  mode 0 forward, 1 data gradient.  Returns 0 on success,
 // a negative DINCAE_E* code, or 1 when the shape does not fit and the caller should use
-// the FFMA kernel.  stage_planes: planes that go through the 2x2 reduction (pool / upsample
-// gradient).
-int launch_conv_mma(int mode, const ConvParams& P, int stage_planes, cudaStream_t st);
+// the FFMA kernel.
+int launch_conv_tc(int mode, const ConvParams& P, cudaStream_t st);
 
 }  // namespace dincae

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     const float4* __restrict__ xrec, const float2* __restrict__ xtrue, size_t n,
     int truth_uncertain, float neg_slope, const int32_t* __restrict__ n_noncloud,
     float4* __restrict__ g_out, double* __restrict__ sums, float* __restrict__ loss_out,
-    LossWork* __restrict__ work) {
+    LossWork* __restrict__ work, int round_tf32) {
   const bool normalise = n_noncloud != nullptr;
   const float nn = normalise ? (float)(*n_noncloud) : 1.0f;
   const float inv_n = 1.0f / nn;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     }
     ga *= inv_n * (r.x > 0.f ? 1.0f : neg_slope);
     gb *= inv_n * (r.y > 0.f ? 1.0f : neg_slope);
-    g_out[i] = make_float4(ga, gb, 0.f, 0.f);
+    g_out[i] = round_tf32 ? make_float4(to_tf32(ga), to_tf32(gb), 0.f, 0.f) : make_float4(ga, gb, 0.f, 0.f);
   }
   __shared__ double red[8][4];
   double v[4] = {(double)s_log, (double)s_sq, (double)s_d2, (double)s_w};
@@ -149,6 +149,6 @@ extern "C" int dincae_head_loss(const float* xrec, const float* xtrue, int B, in
   head_loss_kernel<<<loss_blocks(n), 256, 0, st>>>(
       reinterpret_cast<const float4*>(xrec), reinterpret_cast<const float2*>(xtrue), n,
       truth_uncertain, neg_slope, n_noncloud, reinterpret_cast<float4*>(g_out), sums, loss_out,
-      reinterpret_cast<LossWork*>(workspace));
+      reinterpret_cast<LossWork*>(workspace), g_conv_backend == 1);
   return check_launch();
 }

@@ -9,9 +9,21 @@ import pytest
 import torch
 
 from oracle import datagen_np
-from tests.util import T0, dev, from_p4, random_cube
+from tests.util import T0, dev, from_p4, random_cube, tf32_round
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def exact_inputs():
+    """Bit-exact parity is checked with the fp32 conv back end selected; with the tensor-core
+    back end the builder rounds xin to TF32 on store (test_tensor_core_backend_rounds_inputs)."""
+    from dincae_b200 import _lib
+    lib = _lib.load()
+    lib.dincae_set_conv_backend(0)
+    yield
+    lib.dincae_set_conv_backend(1)
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "datagen_*.npz")))
 
 
@@ -138,3 +150,25 @@ def test_philox_jitter_statistics_and_determinism():
     assert abs(d.mean()) < 3e-3 and abs(d.std() - 0.1) < 3e-3
     for ch in (6, 8):
         assert a[..., ch].std() > 0
+
+
+def test_tensor_core_backend_rounds_inputs():
+    """Under conv back end 1 xin is the TF32 rounding (nearest, ties away) of the exact
+    result; xtrue and the observed-pixel count are untouched."""
+    from dincae_b200 import _lib
+    from dincae_b200.data import DeviceCube
+    rs = np.random.RandomState(11)
+    T, H, W = 7, 9, 13
+    lon, lat, time, fields = random_cube(rs, T, H, W, 1)
+    missing = [np.ma.getmaskarray(f) for f in fields]
+    cube = DeviceCube(lon, lat, time, fields, missing, [1.3], 3)
+    frames = [0, 3, 6, 2]
+    clouds = [1, 5, 0, 4]
+    noise = rs.standard_normal((4, 3, H, W))
+    exact = build(cube, frames, clouds, noise, [0.05], 4)
+    lib = _lib.load()
+    lib.dincae_set_conv_backend(1)
+    rounded = build(cube, frames, clouds, noise, [0.05], 4)
+    assert np.array_equal(rounded[0], tf32_round(exact[0]))
+    assert np.array_equal(rounded[1], exact[1])
+    assert rounded[2] == exact[2]

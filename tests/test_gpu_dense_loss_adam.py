@@ -13,6 +13,18 @@ from tests.util import dev, rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def fp32_backend():
+    """These kernels are fp32; with the tensor-core conv back end selected the loss head rounds
+    the gradient it hands to the last convolution to TF32 (checked in
+    test_loss_head_rounds_gradient_for_tensor_core_backend)."""
+    from dincae_b200 import _lib
+    lib = _lib.load()
+    lib.dincae_set_conv_backend(0)
+    yield
+    lib.dincae_set_conv_backend(1)
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -91,6 +103,15 @@ def test_head_and_loss(B, H, W, uncertain):
     assert sums[3].item() == n.item()
     assert rel_err(gout[:, 0, :, :, :2].cpu().numpy(), pr.grad.numpy()) < 2e-5
     assert float(gout[..., 2:].abs().max()) == 0.0
+    # tensor-core conv back end: the same gradient, rounded to TF32 on store
+    from tests.util import tf32_round
+    lib.dincae_set_conv_backend(1)
+    g1 = torch.zeros_like(gout)
+    check(lib.dincae_head_loss(ptr(xd), ptr(xt), B, H, W, int(uncertain), 0.2, ptr(nn), ptr(g1),
+                               ptr(sums), ptr(lout), ptr(ws), ws_bytes, stream()))
+    torch.cuda.synchronize()
+    lib.dincae_set_conv_backend(0)
+    assert np.array_equal(g1.cpu().numpy(), tf32_round(gout.cpu().numpy()))
     # un-normalised mode: gradient * 1/n equals the normalised one
     g2 = torch.zeros_like(gout)
     check(lib.dincae_head_loss(ptr(xd), ptr(xt), B, H, W, int(uncertain), 0.2, None, ptr(g2),

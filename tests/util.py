@@ -41,3 +41,13 @@ def random_cube(rs, T, H, W, nf, frac=0.4):
         m[:, 0, 0] = True
         fields.append(np.ma.masked_array(d, m))
     return lon, lat, time, fields
+
+
+def tf32_round(a):
+    """numpy/torch float32 -> nearest TF32-representable float32 (10 mantissa bits, ties away
+    from zero) == the device's to_tf32() / cvt.rna.tf32.f32."""
+    is_t = isinstance(a, torch.Tensor)
+    x = a.detach().cpu().numpy() if is_t else np.asarray(a)
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    return torch.from_numpy(r.copy()) if is_t else r
