@@ -472,6 +472,9 @@ extern "C" size_t dincae_conv3x3_wgrad_workspace(int c0p, int c1p, int cout_pad,
     const size_t need = (size_t)nblk * ((size_t)9 * cinp * cout_pad * 4 + cout_pad) * sizeof(float);
     if (need > worst) worst = need;
   }
+  // tensor-core path: at most one partial per SM (148 on B200; 160 leaves head-room)
+  const size_t tc_need = (size_t)160 * ((size_t)9 * cinp * cout_pad * 4 + cout_pad) * sizeof(float);
+  if (tc_need > worst) worst = tc_need;
   return align_up(worst, 256);
 }
 
@@ -488,14 +491,26 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
   int rc = fill_src_grad(P.g, g_full, g_pool, sign, neg_slope, gp, H, W);
   if (rc) return rc;
   P.B = B; P.H = H; P.W = W; P.cinp = P.u.planes(); P.gp = gp; P.cout_pad = cout_pad;
+  cudaStream_t st = (cudaStream_t)stream;
+  P.wsize = 9 * P.cinp * cout_pad * 4;
+  if (g_conv_backend == 1) {
+    int nb = 0;
+    rc = wgrad_tc(P.u, P.g, B, H, W, P.cinp, gp, cout_pad, reinterpret_cast<float*>(workspace),
+                  workspace_bytes, &nb, st);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      const int total = P.wsize + cout_pad;
+      wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nb,
+                                                               P.wsize, cout_pad, gp * 4, dw, db);
+      return check_launch();
+    }
+  }
   int nblk;
   wgrad_plan(P.cinp, gp, B, H, W, P.cib, P.cob, P.panels_ci, P.panels_co, nblk);
-  P.wsize = 9 * P.cinp * cout_pad * 4;
   const size_t need = (size_t)nblk * ((size_t)P.wsize + cout_pad) * sizeof(float);
   if (need > workspace_bytes) return DINCAE_ENOSPC;
   P.partial = reinterpret_cast<float*>(workspace);
   const size_t smem = ((size_t)P.cib * WG_PH * WG_PW + (size_t)P.cob * WG_TH * WG_TW) * sizeof(float4);
-  cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(nblk, P.panels_ci * P.panels_co);
   conv3x3_wgrad_kernel<<<grid, 256, smem, st>>>(P);
   rc = check_launch();

@@ -32,4 +32,10 @@ struct ConvParams {
 // the FFMA kernel.
 int launch_conv_tc(int mode, const ConvParams& P, cudaStream_t st);
 
+// Tensor-core weight gradient (conv_wgrad_tc.cu): writes `*nblk` partials of
+// (9*cinp*cout_pad*4 + cout_pad) floats into `partial`; the caller reduces them.  Same return
+// convention as launch_conv_tc (1 = shape not taken).
+int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, int gp, int cout_pad,
+             float* partial, size_t partial_bytes, int* nblk, cudaStream_t st);
+
 }  // namespace dincae

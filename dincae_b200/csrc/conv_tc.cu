@@ -61,34 +61,6 @@ struct TcParams {
   TcPlan m;
 };
 
-// Predicated read-only loads as single instructions: the loader issues all loads of a stage
-// back to back (no branches between them), then converts and stores.
-__device__ __forceinline__ float4 ldg_f4_pred(const float4* p, bool ok) {
-  float4 v;
-  asm("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n"
-      "mov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\nmov.f32 %3, 0f00000000;\n"
-      "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n}"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)ok));
-  return v;
-}
-__device__ __forceinline__ unsigned ldg_u16_pred(const uint16_t* p, bool ok) {
-  unsigned short v;
-  asm("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\nmov.b16 %0, 0;\n@p ld.global.nc.u16 %0, [%1];\n}"
-      : "=h"(v) : "l"(p), "r"((int)ok));
-  return v;
-}
-
-// un-pool + leaky-ReLU gradient applied to a loaded half-resolution gradient (SRCM 1)
-__device__ __forceinline__ float4 tc_unpool(float4 g, unsigned bits, int x, int W, float inv_y, float slope) {
-  const float inv = inv_y * ((2 * (x >> 1) + 1 < W) ? 0.5f : 1.0f);
-  bits >>= 4 * (x & 3);
-  g.x = g.x * inv * ((bits & 1u) ? 1.0f : slope);
-  g.y = g.y * inv * ((bits & 2u) ? 1.0f : slope);
-  g.z = g.z * inv * ((bits & 4u) ? 1.0f : slope);
-  g.w = g.w * inv * ((bits & 8u) ? 1.0f : slope);
-  return g;
-}
-
 template <int MODE>
 __device__ __forceinline__ void tc_load_w(float4 (&wv)[TC_WB], int base, int tid, int k0, int Kp,
                                           const ConvParams& P, const TcPlan& L) {

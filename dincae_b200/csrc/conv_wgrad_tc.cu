@@ -1,0 +1,359 @@
+// Weight + bias gradient of the 3x3 convolutions on the 5th-gen tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+//   dW[dy][dx][ci][co] = sum over pixels  U[y+dy-1][x+dx-1][ci] * G[y][x][co]
+//
+// is a GEMM whose reduction dimension is the PIXEL index, so both operands are needed
+// "K-major" with pixels contiguous -- the transpose of the planar-4 activation layout (tf32
+// MN-major descriptors are not usable without swizzle: tools/umma_decode.cu).  The loader
+// warps therefore transpose on the way into shared memory (float4 of 4 channels in, 4 scalar
+// stores out) into [pixel group of 4][channel group of 8][8][4] tiles: core matrices of
+// 8 channels x 4 pixels (128 B) at a 144-byte pitch (SBO), pixel groups at an odd multiple of
+// 16 bytes (LBO) so that the scalar stores of a warp (32 consecutive pixels of one channel)
+// hit 32 different banks.  MMA rows past the real channel groups (M is 64 or 128 whatever
+// Cin) alias the following pixel groups: in bounds, and their D rows are never read.
+//
+// Per K step (8 pixels of one image row) and per dy one MMA:
+//   A = U rows  (M = input channels, start address shifted by dy rows),
+//   B = three dx-shifted copies of G stacked along N (N = 3 * Cout8), written by the loader,
+// so that 3 MMAs per 8 pixels produce all 9 taps.  One extra A row of constant ones gives the
+// bias gradient (sum of G) as row `ones_row` of the dy = 1 accumulator.  Each CTA keeps its
+// three accumulators in TMEM over all its tiles and writes ONE partial at the end;
+// wgrad_reduce_kernel (conv.cu) sums the partials in fixed order (deterministic).
+#include "common.cuh"
+#include "conv_params.cuh"
+#include "umma.cuh"
+
+namespace dincae {
+
+constexpr int WG_LOAD_WARPS = 12;
+constexpr int WG_MMA_WARP = WG_LOAD_WARPS;
+constexpr int WG_THREADS = 32 * (WG_LOAD_WARPS + 1);
+constexpr int WG_STAGES = 2;
+constexpr int WG_CM = 36;                 // floats per (8 channel x 4 pixel) core matrix incl. pad
+constexpr int WG_MAX_ITEMS = 512;
+
+struct WgTcParams {
+  ConvSrc u;                // conv input (concat / upsample fused)
+  ConvSrc g;                // gradient w.r.t. the pre-activation (direct or un-pooled)
+  int B, H, W;
+  int kp, gp;               // planes of U and G
+  int cinp, cout_pad;       // packed weight shape [9][cinp][cout_pad][4]
+  int wsize;                // 9 * cinp * cout_pad * 4
+  float* partial;           // [gridDim.x][wsize + cout_pad]
+  // plan
+  int R, TW, n_row_blocks, n_tiles;
+  int cgu, cgg;             // channel groups (of 8) of U (incl. ones row) and of one G copy
+  int M, N, ones_row;
+  int npg_u, npg_g;         // pixel groups (of 4) in the U / G tile
+  int pitch_u, pitch_g;     // floats per pixel group (all channel groups + bank pad)
+  int u_floats, stage_floats;
+  int n_items_u, n_items;   // loader row items per stage
+  int tmem_cols;
+};
+
+__device__ __forceinline__ void wg_store_t(float* tile, int pitch, int plane, int p, float4 v) {
+  // channels 4*plane .. 4*plane+3 of pixel p -> [p/4][plane/2][(plane&1)*4 + j][p%4]
+  float* d = tile + (p >> 2) * pitch + (plane >> 1) * WG_CM + ((plane & 1) << 4) + (p & 3);
+  d[0] = v.x; d[4] = v.y; d[8] = v.z; d[12] = v.w;
+}
+
+template <int GMODE>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const WgTcParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t full_bar[WG_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[WG_STAGES];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_holder;
+  __shared__ uint16_t item_tab[WG_MAX_ITEMS];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: zero the ring, ones row, item table, barriers, TMEM ------------------
+  for (int i = tid; i < WG_STAGES * P.stage_floats; i += WG_THREADS) ring[i] = 0.f;
+  for (int i = tid; i < P.n_items; i += WG_THREADS) {
+    // item = one row of one plane: U items (plane, row of R+2) first, then G items (plane, row of R)
+    int is_g = i >= P.n_items_u, k = is_g ? i - P.n_items_u : i;
+    const int rows = is_g ? P.R : P.R + 2;
+    item_tab[i] = (uint16_t)((is_g << 15) | ((k / rows) << 6) | (k % rows));
+  }
+  __syncthreads();
+  {
+    const int cg = P.ones_row >> 3, c8 = P.ones_row & 7;
+    for (int s = 0; s < WG_STAGES; ++s)
+      for (int i = tid; i < P.npg_u * 4; i += WG_THREADS)
+        ring[s * P.stage_floats + (i >> 2) * P.pitch_u + cg * WG_CM + c8 * 4 + (i & 3)] = 1.0f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full_bar[s], WG_LOAD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(&tmem_holder)), "r"(P.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const int TW = P.TW, R = P.R;
+
+  if (warp < WG_LOAD_WARPS) {
+    // =============================== transposing loader ======================================
+    const ConvSrc U = P.u;
+    const ConvSrc G = P.g;
+    const int shu = U.half0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int b = tile / P.n_row_blocks;
+      const int y0 = (tile - b * P.n_row_blocks) * R;
+      float* Ut = ring + s * P.stage_floats;
+      float* Gt = Ut + P.u_floats;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      for (int it = warp; it < P.n_items; it += WG_LOAD_WARPS) {
+        const unsigned e = item_tab[it];
+        const int plane = (e >> 6) & 0x1ff, r = e & 63;
+        float4 v[4];
+        if (!(e & 0x8000u)) {
+          // ---- U row: y = y0 - 1 + r, all TW columns (zero outside the image) ----------------
+          const int y = y0 - 1 + r;
+          const bool rok = (unsigned)y < (unsigned)P.H;
+          const float4* base;
+          int sh = 0;
+          if (plane < U.p0) {
+            sh = shu;
+            base = U.s0 + ((size_t)((b * U.p0 + plane) * (sh ? U.Hh : U.H) + (y >> sh))) * (sh ? U.Wh : U.W);
+          } else {
+            base = U.s1 + ((size_t)((b * U.p1 + (plane - U.p0)) * U.H + y)) * U.W;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int x = lane + 32 * u;
+            v[u] = ldg_f4_pred(base + (x >> sh), rok && x < P.W);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int x = lane + 32 * u;
+            if (x < TW) wg_store_t(Ut, P.pitch_u, plane, r * TW + x, to_tf32(v[u]));
+          }
+        } else {
+          // ---- G row: y = y0 + r; three copies shifted by dx - 1 columns -----------------------
+          const int y = y0 + r;
+          const bool rok = y < P.H;
+          unsigned sb[4] = {0, 0, 0, 0};
+          if (GMODE == 0) {
+            const float4* base = G.s0 + ((size_t)((b * G.p0 + plane) * G.H + y)) * G.W;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int x = lane + 32 * u;
+              v[u] = ldg_f4_pred(base + x, rok && x < P.W);
+            }
+          } else {
+            const float4* base = G.s0 + ((size_t)((b * G.p0 + plane) * G.Hh + (y >> 1))) * G.Wh;
+            const uint16_t* sg = G.sign + ((size_t)((b * G.p0 + plane) * G.H + y)) * G.Wq;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int x = lane + 32 * u;
+              v[u] = ldg_f4_pred(base + (x >> 1), rok && x < P.W);
+              sb[u] = ldg_u16_pred(sg + (x >> 2), rok && x < P.W);
+            }
+          }
+          const float inv_y = (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int x = lane + 32 * u;
+            if (x >= TW) continue;
+            float4 t = v[u];
+            if (GMODE == 1) t = tc_unpool(t, sb[u], x, P.W, inv_y, G.slope);
+            t = to_tf32(t);
+            const int p = r * TW + x;
+            // copy dx holds G[x' - dx + 1] at column x', i.e. G[x] lands at column x + dx - 1
+            // (the cells no G[x] lands on, column TW-1 of copy 0 and column 0 of copy 2, stay
+            // zero from the initial clear)
+            if (x >= 1) wg_store_t(Gt, P.pitch_g, plane, p - 1, t);
+            wg_store_t(Gt, P.pitch_g, 2 * P.cgg + plane, p, t);
+            if (x + 1 < TW) wg_store_t(Gt, P.pitch_g, 4 * P.cgg + plane, p + 1, t);
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // =============================== MMA issuer ===============================================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.N >> 3) << 17) |
+                           ((uint32_t)(P.M >> 4) << 24);
+    const uint64_t a_hi = umma_desc(0u, (uint32_t)P.pitch_u * 4u, WG_CM * 4u);
+    const uint64_t b_hi = umma_desc(0u, (uint32_t)P.pitch_g * 4u, WG_CM * 4u);
+    const uint32_t ua = (uint32_t)(P.pitch_u >> 2), ga = (uint32_t)(P.pitch_g >> 2);   // 16-byte units
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t first = 0;                         // 0 until the accumulators hold a value
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t u_lo = smem_u32(ring + s * P.stage_floats) >> 4;
+        const uint32_t g_lo = u_lo + (uint32_t)(P.u_floats >> 2);
+        for (int ry = 0; ry < R; ++ry) {
+          for (int x8 = 0; x8 < TW; x8 += 8) {
+            const uint32_t bt = g_lo + (uint32_t)((ry * TW + x8) >> 2) * ga;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t at = u_lo + (uint32_t)(((ry + dy) * TW + x8) >> 2) * ua;
+              umma_tf32(tmem_base + (uint32_t)(dy * P.N), a_hi | (uint64_t)(at & 0x3fffu),
+                        b_hi | (uint64_t)(bt & 0x3fffu), idesc, first);
+            }
+            first = 1u;
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+      if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (elect_one()) umma_commit(&done_bar);
+    __syncwarp();
+  }
+
+  // =============================== epilogue (loader warps 0-3) ================================
+  if (warp < 4) {
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    const int q = warp;
+    const int m = P.M == 64 ? (lane < 16 ? 16 * q + lane : -1) : 32 * q + lane;
+    float* out = P.partial + (size_t)blockIdx.x * (P.wsize + P.cout_pad);
+    const int cout8 = P.cgg * 8;
+    const bool row_w = m >= 0 && m < 4 * P.kp;
+    const bool row_b = m == P.ones_row;
+    for (int dy = 0; dy < 3; ++dy) {
+      for (int dx = 0; dx < 3; ++dx) {
+        const int tap = dy * 3 + dx;
+        for (int c0 = 0; c0 < cout8; c0 += 8) {
+          float a[8];
+          tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dy * P.N + dx * cout8 + c0), a);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int co = c0 + t;
+            if (co >= P.gp * 4) continue;
+            if (row_w) out[((size_t)(tap * P.cinp + (m >> 2)) * P.cout_pad + co) * 4 + (m & 3)] = a[t];
+            if (row_b && tap == 4) out[P.wsize + co] = a[t];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "r"(P.tmem_cols));
+  }
+}
+
+static int wg_pow2_cols(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Shape plan; false when the layer does not fit this path (caller uses the FFMA kernel).
+bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
+  const int Cin4 = 4 * P.kp;
+  if (P.W > 128 || P.kp > 31 || P.gp > 21) return false;
+  P.TW = (P.W + 7) / 8 * 8;
+  P.ones_row = Cin4;                                // first row after the packed channels
+  P.cgu = (Cin4 + 1 + 7) / 8;
+  P.cgg = (P.gp * 4 + 7) / 8;
+  P.M = P.cgu * 8 <= 64 ? 64 : 128;
+  P.N = 3 * P.cgg * 8;
+  if (P.M == 128 && (P.N & 15)) {                   // M = 128 needs N % 16 == 0: pad one group
+    P.cgg += 1;
+    P.N = 3 * P.cgg * 8;
+  }
+  if (P.N > 256 || 3 * P.N > 512) return false;
+  if ((long long)P.B * (P.kp > P.gp ? P.kp : P.gp) * P.H * P.W >= (1ll << 31)) return false;
+  P.tmem_cols = wg_pow2_cols(3 * P.N);
+  // pixel-group pitch: all channel groups, padded to an odd number of 16-byte units
+  P.pitch_u = (P.cgu * 9 + ((P.cgu & 1) ? 0 : 1)) * 4;
+  P.pitch_g = (3 * P.cgg * 9 + (((3 * P.cgg) & 1) ? 0 : 1)) * 4;
+  const int slack = 16 * WG_CM;                     // over-read of the unused MMA row groups
+  // rows per stage: largest R (<= 16) whose two stages fit in ~200 KB
+  int best = 0;
+  for (int R = 1; R <= 16 && R <= P.H; ++R) {
+    const long long uf = (long long)((R + 2) * P.TW / 4) * P.pitch_u + slack;
+    const long long gf = (long long)(R * P.TW / 4) * P.pitch_g + slack;
+    const int items = P.kp * (R + 2) + P.gp * R;
+    if ((uf + gf) * 4 * WG_STAGES <= 200 * 1024 && items <= WG_MAX_ITEMS && R + 2 <= 63) best = R;
+  }
+  if (!best) return false;
+  P.R = best;
+  P.npg_u = (P.R + 2) * P.TW / 4;
+  P.npg_g = P.R * P.TW / 4;
+  P.u_floats = P.npg_u * P.pitch_u + slack;
+  P.stage_floats = P.u_floats + P.npg_g * P.pitch_g + slack;
+  if ((long long)P.stage_floats * 4 * WG_STAGES >= (1 << 18)) return false;
+  P.n_items_u = P.kp * (P.R + 2);
+  P.n_items = P.n_items_u + P.gp * P.R;
+  P.n_row_blocks = (P.H + P.R - 1) / P.R;
+  P.n_tiles = P.B * P.n_row_blocks;
+  (void)sm_count;
+  return true;
+}
+
+static int wgrad_tc_blocks(const WgTcParams& P, int sm_count) {
+  // enough K steps per CTA to amortise the partial write; at most one CTA per SM
+  int nblk = P.n_tiles / 2;
+  if (nblk > sm_count) nblk = sm_count;
+  if (nblk < 1) nblk = 1;
+  return nblk;
+}
+
+int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, int gp, int cout_pad,
+             float* partial, size_t partial_bytes, int* nblk_out, cudaStream_t st) {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  if (u.mode != 0) return 1;
+  WgTcParams P;
+  P.u = u; P.g = g; P.B = B; P.H = H; P.W = W;
+  P.kp = cinp; P.gp = gp; P.cinp = cinp; P.cout_pad = cout_pad;
+  P.wsize = 9 * cinp * cout_pad * 4;
+  P.partial = partial;
+  if (!conv_wgrad_tc_plan(P, sm_count)) return 1;
+  const int nblk = wgrad_tc_blocks(P, sm_count);
+  if ((size_t)nblk * ((size_t)P.wsize + cout_pad) * sizeof(float) > partial_bytes) return DINCAE_ENOSPC;
+  const int gmode = g.mode;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[gmode]) {
+    cudaError_t e = gmode == 0
+        ? cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)
+        : cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return cuda_rc(e);
+    attr_set[gmode] = true;
+  }
+  const size_t smem = (size_t)WG_STAGES * P.stage_floats * 4;
+  if (gmode == 0)
+    conv3x3_wgrad_tc_kernel<0><<<nblk, WG_THREADS, smem, st>>>(P);
+  else
+    conv3x3_wgrad_tc_kernel<1><<<nblk, WG_THREADS, smem, st>>>(P);
+  *nblk_out = nblk;
+  return check_launch();
+}
+
+}  // namespace dincae
