@@ -13,8 +13,8 @@ struct RedWork {
 };
 
 static int red_blocks(size_t n) {
-  size_t b = (n + 2047) / 2048;
-  if (b > 4 * 148) b = 4 * 148;
+  size_t b = (n + 4095) / 4096;
+  if (b > 2 * 148) b = 2 * 148;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -31,12 +31,34 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p,
                                                     RedWork* __restrict__ work) {
   float s = 0.f;
   if (MODE == 0 && denom) grad_scale /= (float)(*denom);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  const bool decay = MODE == 0 && l2_beta != 0.f;
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
+    float4 a;
+    if (MODE == 0) {
+      a = f4_scale(__ldg(reinterpret_cast<const float4*>(g) + i), grad_scale);
+      if (decay && 4 * i < n_decay) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+        a.x = fmaf(l2_beta, q.x, a.x);
+        if (4 * i + 1 < n_decay) a.y = fmaf(l2_beta, q.y, a.y);
+        if (4 * i + 2 < n_decay) a.z = fmaf(l2_beta, q.z, a.z);
+        if (4 * i + 3 < n_decay) a.w = fmaf(l2_beta, q.w, a.w);
+      }
+    } else {
+      a = __ldg(reinterpret_cast<const float4*>(p) + i);
+    }
+    s = fmaf(a.x, a.x, s);
+    s = fmaf(a.y, a.y, s);
+    s = fmaf(a.z, a.z, s);
+    s = fmaf(a.w, a.w, s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {          // tail (n not a multiple of 4)
+    const size_t i = (n4 << 2) + threadIdx.x;
     float v;
     if (MODE == 0) {
       v = g[i] * grad_scale;
-      if (i < n_decay && l2_beta != 0.f) v = fmaf(l2_beta, p[i], v);
+      if (decay && i < n_decay) v = fmaf(l2_beta, p[i], v);
     } else {
       v = p[i];
     }
@@ -55,10 +77,18 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p,
     is_last = atomicAdd(&work->counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
+  if (!is_last) return;
+  // last block: sum the per-block partials in a fixed order (thread k takes k, k+256, ...)
+  __threadfence();
+  double mine = 0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) mine += *((volatile double*)&work->partial[b]);
+  mine = warp_sum(mine);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double t = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += *((volatile double*)&work->partial[b]);
+    for (int w = 0; w < 8; ++w) t += red[w];
     if (MODE == 0) {
       const float norm = (float)sqrt(t);
       float scale = 1.0f;

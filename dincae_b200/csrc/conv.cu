@@ -331,19 +331,33 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams P)
 }
 
 // out[e] = sum over blocks of partial[blk][e]; entries of padded output channels are zero.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int wsize,
-                                    int cout_pad, int gp4, float* __restrict__ dw,
-                                    float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// Eight lanes share an element (lane j takes blocks j, j+8, ...), partial sums are combined
+// in a fixed order by shuffles, so the result does not depend on the run.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nblk,
+                                                           int wsize, int cout_pad, int gp4,
+                                                           float* __restrict__ dw, float* __restrict__ db) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 3, j = t & 7;
   const int total = wsize + cout_pad;
-  if (e >= total) return;
-  int co;
-  if (e < wsize) co = (e >> 2) % cout_pad; else co = e - wsize;
-  float sum = 0.f;
-  if (co < gp4) {
-    for (int k = 0; k < nblk; ++k) sum += partial[(size_t)k * total + e];
+  const bool in = e < total;
+  int co = 0;
+  if (in) co = e < wsize ? (e >> 2) % cout_pad : e - wsize;
+  float s0 = 0.f, s1 = 0.f;
+  if (in && co < gp4) {
+    int k = j;
+    for (; k + 8 < nblk; k += 16) {
+      s0 += __ldg(&partial[(size_t)k * total + e]);
+      s1 += __ldg(&partial[(size_t)(k + 8) * total + e]);
+    }
+    if (k < nblk) s0 += __ldg(&partial[(size_t)k * total + e]);
   }
-  if (e < wsize) dw[e] = sum; else db[co] = sum;
+  float sum = s0 + s1;
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  if (in && j == 0) {
+    if (e < wsize) dw[e] = sum; else db[co] = sum;
+  }
 }
 
 static void fill_src_concat(ConvSrc& s, const float* src0, int c0p, int half0, const float* src1,
@@ -500,7 +514,7 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
     if (rc < 0) return rc;
     if (rc == 0) {
       const int total = P.wsize + cout_pad;
-      wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nb,
+      wgrad_reduce_kernel<<<ceil_div(total * 8, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nb,
                                                                P.wsize, cout_pad, gp * 4, dw, db);
       return check_launch();
     }
@@ -516,7 +530,7 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
   rc = check_launch();
   if (rc) return rc;
   const int total = P.wsize + cout_pad;
-  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(P.partial, nblk, P.wsize, cout_pad,
+  wgrad_reduce_kernel<<<ceil_div(total * 8, 256), 256, 0, st>>>(P.partial, nblk, P.wsize, cout_pad,
                                                            gp * 4, dw, db);
   return check_launch();
 }

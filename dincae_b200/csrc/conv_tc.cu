@@ -486,9 +486,20 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
           } else {
             // planes below c_lo: gradient of the x2 nearest upsample (2x2 sum) times the previous
             // activation's slope; planes from c_lo on: skip gradient at full resolution
-            float4 h[4];
+            float4 h[4], side[4];
+            // side inputs of the four planes (previous activation for its slope, or the skip
+            // gradient to add) are requested first: their latency hides behind the shuffles
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) h[qq] = valid ? a[qq] : f4_zero();
+            for (int qq = 0; qq < 4; ++qq) {
+              const int p = p0 + qq;
+              h[qq] = valid ? a[qq] : f4_zero();
+              const bool lo = p < P.c_lo;
+              const float4* sp = lo ? P.prev_act + (o_half + p * s_half + 4 * j)
+                                    : P.dx_add + (o_hi + (p - P.c_lo) * s_full + 8 * j);
+              const bool want = lo ? (P.prev_act != nullptr && store_lane && valid)
+                                   : (P.dx_add != nullptr && valid && p < P.out_planes);
+              side[qq] = ldg_f4_pred(sp, want);
+            }
             if (p0 < P.c_lo) {
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
@@ -513,7 +524,7 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
                   const int at = o_half + p * s_half + 4 * j;
                   float4 t = h[qq];
                   if (P.prev_act) {
-                    const float4 pa = __ldg(&P.prev_act[at]);
+                    const float4 pa = side[qq];
                     t.x *= pa.x > 0.f ? 1.0f : P.prev_slope;
                     t.y *= pa.y > 0.f ? 1.0f : P.prev_slope;
                     t.z *= pa.z > 0.f ? 1.0f : P.prev_slope;
@@ -524,7 +535,7 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
               } else if (p < P.out_planes && valid) {
                 const int at = o_hi + (p - P.c_lo) * s_full + 8 * j;
                 float4 t = a[qq];
-                if (P.dx_add) t = f4_add(t, __ldg(&P.dx_add[at]));
+                if (P.dx_add) t = f4_add(t, side[qq]);
                 P.dx_hi[at] = to_tf32(t);
               }
             }

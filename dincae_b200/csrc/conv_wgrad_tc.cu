@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "conv_params.cuh"
 #include "umma.cuh"
+#include <math.h>
 
 namespace dincae {
 
@@ -48,7 +49,9 @@ struct WgTcParams {
   int npg_u, npg_g;         // pixel groups (of 4) in the U / G tile
   int pitch_u, pitch_g;     // floats per pixel group (all channel groups + bank pad)
   int u_floats, stage_floats;
-  int n_items_u, n_items;   // loader row items per stage
+  int n_items_u, n_items;   // loader items per stage (plane x 128-pixel chunk)
+  int chunks_u, chunks_g;
+  unsigned inv_tw;          // ceil(2^32 / TW): p / TW == __umulhi(p, inv_tw) for the p used here
   int tmem_cols;
 };
 
@@ -56,6 +59,104 @@ __device__ __forceinline__ void wg_store_t(float* tile, int pitch, int plane, in
   // channels 4*plane .. 4*plane+3 of pixel p -> [p/4][plane/2][(plane&1)*4 + j][p%4]
   float* d = tile + (p >> 2) * pitch + (plane >> 1) * WG_CM + ((plane & 1) << 4) + (p & 3);
   d[0] = v.x; d[4] = v.y; d[8] = v.z; d[12] = v.w;
+}
+
+struct WgPass {
+  int tile, it;
+};
+
+__device__ __forceinline__ WgPass wg_next(WgPass c, int n_pad, int grid) {
+  c.it += WG_LOAD_WARPS;
+  if (c.it >= n_pad) {
+    c.it -= (c.it / WG_LOAD_WARPS) * WG_LOAD_WARPS;      // back to this warp's first item
+    c.tile += grid;
+  }
+  return c;
+}
+
+// Issue the 4 loads of one pass (item c.it of tile c.tile) of this lane.  All offsets are
+// 32-bit (the plan rejects tensors of 2^31 float4 or more).
+template <int GMODE>
+__device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, int lane,
+                                         const uint16_t* item_tab, float4 (&v)[4], unsigned (&sb)[4]) {
+  const bool on = c.it < P.n_items;
+  const unsigned e = on ? item_tab[c.it] : 0u;
+  const int plane = (e >> 6) & 0x1ff, chunk = e & 63;
+  const bool is_g = (e & 0x8000u) != 0;
+  const int b = c.tile / P.n_row_blocks;
+  const int y0 = (c.tile - b * P.n_row_blocks) * P.R;
+  const ConvSrc& U = P.u;
+  const ConvSrc& G = P.g;
+  // plane base offsets (float4 units), resolved once per pass
+  const float4* ubase;
+  int ush = 0, uw = U.W;
+  if (plane < U.p0) {
+    ush = U.half0;
+    uw = ush ? U.Wh : U.W;
+    ubase = U.s0 + (b * U.p0 + plane) * (ush ? U.Hh * U.Wh : U.H * U.W);
+  } else {
+    ubase = U.s1 + (b * U.p1 + (plane - U.p0)) * (U.H * U.W);
+  }
+  const float4* gbase = G.s0 + (b * G.p0 + plane) * (GMODE == 0 ? G.H * G.W : G.Hh * G.Wh);
+  const uint16_t* sbase = GMODE == 1 ? G.sign + (b * G.p0 + plane) * (G.H * G.Wq) : nullptr;
+  const int npix = is_g ? P.R * P.TW : (P.R + 2) * P.TW;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int p = chunk * 128 + lane + 32 * u;
+    const int r = (int)__umulhi((unsigned)p, P.inv_tw), x = p - r * P.TW;
+    sb[u] = 0;
+    if (!is_g) {
+      const int y = y0 - 1 + r;
+      const bool ok = on && p < npix && (unsigned)y < (unsigned)P.H && x < P.W;
+      v[u] = ldg_f4_pred(ubase + ((y >> ush) * uw + (x >> ush)), ok);
+    } else {
+      const int y = y0 + r;
+      const bool ok = on && p < npix && y < P.H && x < P.W;
+      if (GMODE == 0) {
+        v[u] = ldg_f4_pred(gbase + (y * G.W + x), ok);
+      } else {
+        v[u] = ldg_f4_pred(gbase + ((y >> 1) * G.Wh + (x >> 1)), ok);
+        sb[u] = ldg_u16_pred(sbase + (y * G.Wq + (x >> 2)), ok);
+      }
+    }
+  }
+}
+
+// Convert (TF32) and store one pass into its stage: U transposed, G as three dx-shifted copies.
+template <int GMODE>
+__device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, int lane,
+                                          const uint16_t* item_tab, float* stage,
+                                          const float4 (&v)[4], const unsigned (&sb)[4]) {
+  if (c.it >= P.n_items) return;
+  const unsigned e = item_tab[c.it];
+  const int plane = (e >> 6) & 0x1ff, chunk = e & 63;
+  const bool is_g = (e & 0x8000u) != 0;
+  const int TW = P.TW;
+  float* Ut = stage;
+  float* Gt = stage + P.u_floats;
+  const int b = c.tile / P.n_row_blocks;
+  const int y0 = (c.tile - b * P.n_row_blocks) * P.R;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int p = chunk * 128 + lane + 32 * u;
+    if (!is_g) {
+      if (p < (P.R + 2) * TW) wg_store_t(Ut, P.pitch_u, plane, p, to_tf32(v[u]));
+    } else if (p < P.R * TW) {
+      const int r = (int)__umulhi((unsigned)p, P.inv_tw), x = p - r * TW;
+      float4 t = v[u];
+      if (GMODE == 1) {
+        const int y = y0 + r;
+        t = tc_unpool(t, sb[u], x, P.W, (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f, P.g.slope);
+      }
+      t = to_tf32(t);
+      // copy dx holds G[x' - dx + 1] at column x', i.e. G[x] lands at column x + dx - 1 (the
+      // cells no G[x] lands on, column TW-1 of copy 0 and column 0 of copy 2, stay zero from
+      // the initial clear)
+      if (x >= 1) wg_store_t(Gt, P.pitch_g, plane, p - 1, t);
+      wg_store_t(Gt, P.pitch_g, 2 * P.cgg + plane, p, t);
+      if (x + 1 < TW) wg_store_t(Gt, P.pitch_g, 4 * P.cgg + plane, p + 1, t);
+    }
+  }
 }
 
 template <int GMODE>
@@ -71,12 +172,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: zero the ring, ones row, item table, barriers, TMEM ------------------
-  for (int i = tid; i < WG_STAGES * P.stage_floats; i += WG_THREADS) ring[i] = 0.f;
+  for (int i = tid; i < (WG_STAGES * P.stage_floats) >> 2; i += WG_THREADS)
+    reinterpret_cast<float4*>(ring)[i] = f4_zero();
   for (int i = tid; i < P.n_items; i += WG_THREADS) {
-    // item = one row of one plane: U items (plane, row of R+2) first, then G items (plane, row of R)
+    // item = (plane, 128-pixel chunk): U items first, then G items
     int is_g = i >= P.n_items_u, k = is_g ? i - P.n_items_u : i;
-    const int rows = is_g ? P.R : P.R + 2;
-    item_tab[i] = (uint16_t)((is_g << 15) | ((k / rows) << 6) | (k % rows));
+    const int chunks = is_g ? P.chunks_g : P.chunks_u;
+    item_tab[i] = (uint16_t)((is_g << 15) | ((k / chunks) << 6) | (k % chunks));
   }
   __syncthreads();
   {
@@ -107,87 +209,44 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
 
   if (warp < WG_LOAD_WARPS) {
     // =============================== transposing loader ======================================
-    const ConvSrc U = P.u;
-    const ConvSrc G = P.g;
-    const int shu = U.half0;
+    // Item = 128 consecutive pixels (tile-linear index p = row * TW + x) of one plane.  The
+    // warp's items of all its tiles form one stream of passes that is software-pipelined: the
+    // loads of pass n+1 (4 float4 per lane) are in flight while pass n is converted and
+    // stored, across stage and tile boundaries, so the memory latency is paid once.
+    const int n_pad = P.n_items > WG_LOAD_WARPS ? P.n_items : WG_LOAD_WARPS;   // every warp arrives per tile
+    WgPass cur, nxt;
+    cur.tile = blockIdx.x; cur.it = warp;
+    float4 va[4], vb[4];
+    unsigned sa[4], sbb[4];
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      const int b = tile / P.n_row_blocks;
-      const int y0 = (tile - b * P.n_row_blocks) * R;
-      float* Ut = ring + s * P.stage_floats;
-      float* Gt = Ut + P.u_floats;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      for (int it = warp; it < P.n_items; it += WG_LOAD_WARPS) {
-        const unsigned e = item_tab[it];
-        const int plane = (e >> 6) & 0x1ff, r = e & 63;
-        float4 v[4];
-        if (!(e & 0x8000u)) {
-          // ---- U row: y = y0 - 1 + r, all TW columns (zero outside the image) ----------------
-          const int y = y0 - 1 + r;
-          const bool rok = (unsigned)y < (unsigned)P.H;
-          const float4* base;
-          int sh = 0;
-          if (plane < U.p0) {
-            sh = shu;
-            base = U.s0 + ((size_t)((b * U.p0 + plane) * (sh ? U.Hh : U.H) + (y >> sh))) * (sh ? U.Wh : U.W);
-          } else {
-            base = U.s1 + ((size_t)((b * U.p1 + (plane - U.p0)) * U.H + y)) * U.W;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int x = lane + 32 * u;
-            v[u] = ldg_f4_pred(base + (x >> sh), rok && x < P.W);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int x = lane + 32 * u;
-            if (x < TW) wg_store_t(Ut, P.pitch_u, plane, r * TW + x, to_tf32(v[u]));
-          }
-        } else {
-          // ---- G row: y = y0 + r; three copies shifted by dx - 1 columns -----------------------
-          const int y = y0 + r;
-          const bool rok = y < P.H;
-          unsigned sb[4] = {0, 0, 0, 0};
-          if (GMODE == 0) {
-            const float4* base = G.s0 + ((size_t)((b * G.p0 + plane) * G.H + y)) * G.W;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int x = lane + 32 * u;
-              v[u] = ldg_f4_pred(base + x, rok && x < P.W);
-            }
-          } else {
-            const float4* base = G.s0 + ((size_t)((b * G.p0 + plane) * G.Hh + (y >> 1))) * G.Wh;
-            const uint16_t* sg = G.sign + ((size_t)((b * G.p0 + plane) * G.H + y)) * G.Wq;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int x = lane + 32 * u;
-              v[u] = ldg_f4_pred(base + (x >> 1), rok && x < P.W);
-              sb[u] = ldg_u16_pred(sg + (x >> 2), rok && x < P.W);
-            }
-          }
-          const float inv_y = (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int x = lane + 32 * u;
-            if (x >= TW) continue;
-            float4 t = v[u];
-            if (GMODE == 1) t = tc_unpool(t, sb[u], x, P.W, inv_y, G.slope);
-            t = to_tf32(t);
-            const int p = r * TW + x;
-            // copy dx holds G[x' - dx + 1] at column x', i.e. G[x] lands at column x + dx - 1
-            // (the cells no G[x] lands on, column TW-1 of copy 0 and column 0 of copy 2, stay
-            // zero from the initial clear)
-            if (x >= 1) wg_store_t(Gt, P.pitch_g, plane, p - 1, t);
-            wg_store_t(Gt, P.pitch_g, 2 * P.cgg + plane, p, t);
-            if (x + 1 < TW) wg_store_t(Gt, P.pitch_g, 4 * P.cgg + plane, p + 1, t);
-          }
-        }
+    if (cur.tile < P.n_tiles) wg_issue<GMODE>(P, cur, lane, item_tab, va, sa);
+    while (cur.tile < P.n_tiles) {
+      // ---- pass A ---------------------------------------------------------------------------
+      nxt = wg_next(cur, n_pad, gridDim.x);
+      if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
+      if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, va, sa);
+      if (nxt.tile != cur.tile) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-      if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+      cur = nxt;
+      if (cur.tile >= P.n_tiles) break;
+      // ---- pass B (buffers swapped) ------------------------------------------------------------
+      nxt = wg_next(cur, n_pad, gridDim.x);
+      if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
+      if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, vb, sbb);
+      if (nxt.tile != cur.tile) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+      }
+      cur = nxt;
     }
   } else {
     // =============================== MMA issuer ===============================================
@@ -205,17 +264,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
       if (elect_one()) {
         const uint32_t u_lo = smem_u32(ring + s * P.stage_floats) >> 4;
         const uint32_t g_lo = u_lo + (uint32_t)(P.u_floats >> 2);
-        for (int ry = 0; ry < R; ++ry) {
-          for (int x8 = 0; x8 < TW; x8 += 8) {
-            const uint32_t bt = g_lo + (uint32_t)((ry * TW + x8) >> 2) * ga;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const uint32_t at = u_lo + (uint32_t)(((ry + dy) * TW + x8) >> 2) * ua;
-              umma_tf32(tmem_base + (uint32_t)(dy * P.N), a_hi | (uint64_t)(at & 0x3fffu),
-                        b_hi | (uint64_t)(bt & 0x3fffu), idesc, first);
-            }
-            first = 1u;
-          }
+        // running descriptor offsets (16-byte units): a K step advances two pixel groups, a
+        // row TW/4 of them; dy shifts the A start by whole rows
+        const uint32_t a_row = (uint32_t)(TW >> 2) * ua, a_k = 2u * ua, b_k = 2u * ga;
+        const int ksteps = R * (TW >> 3);
+        uint32_t at = u_lo, bt = g_lo;
+#pragma unroll 2
+        for (int k = 0; k < ksteps; ++k) {
+          umma_tf32(tmem_base, a_hi | (uint64_t)(at & 0x3fffu), b_hi | (uint64_t)(bt & 0x3fffu), idesc, first);
+          umma_tf32(tmem_base + (uint32_t)P.N, a_hi | (uint64_t)((at + a_row) & 0x3fffu),
+                    b_hi | (uint64_t)(bt & 0x3fffu), idesc, first);
+          umma_tf32(tmem_base + (uint32_t)(2 * P.N), a_hi | (uint64_t)((at + 2u * a_row) & 0x3fffu),
+                    b_hi | (uint64_t)(bt & 0x3fffu), idesc, first);
+          first = 1u;
+          at += a_k;
+          bt += b_k;
         }
         umma_commit(&empty_bar[s]);
       }
@@ -294,8 +357,9 @@ bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
   for (int R = 1; R <= 16 && R <= P.H; ++R) {
     const long long uf = (long long)((R + 2) * P.TW / 4) * P.pitch_u + slack;
     const long long gf = (long long)(R * P.TW / 4) * P.pitch_g + slack;
-    const int items = P.kp * (R + 2) + P.gp * R;
-    if ((uf + gf) * 4 * WG_STAGES <= 200 * 1024 && items <= WG_MAX_ITEMS && R + 2 <= 63) best = R;
+    const int cu = ((R + 2) * P.TW + 127) / 128, cg = (R * P.TW + 127) / 128;
+    const int items = P.kp * cu + P.gp * cg;
+    if ((uf + gf) * 4 * WG_STAGES <= 200 * 1024 && items <= WG_MAX_ITEMS && cu <= 63) best = R;
   }
   if (!best) return false;
   P.R = best;
@@ -304,8 +368,11 @@ bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
   P.u_floats = P.npg_u * P.pitch_u + slack;
   P.stage_floats = P.u_floats + P.npg_g * P.pitch_g + slack;
   if ((long long)P.stage_floats * 4 * WG_STAGES >= (1 << 18)) return false;
-  P.n_items_u = P.kp * (P.R + 2);
-  P.n_items = P.n_items_u + P.gp * P.R;
+  P.chunks_u = ((P.R + 2) * P.TW + 127) / 128;
+  P.chunks_g = (P.R * P.TW + 127) / 128;
+  P.n_items_u = P.kp * P.chunks_u;
+  P.n_items = P.n_items_u + P.gp * P.chunks_g;
+  P.inv_tw = (unsigned)((0x100000000ull + P.TW - 1) / P.TW);
   P.n_row_blocks = (P.H + P.R - 1) / P.R;
   P.n_tiles = P.B * P.n_row_blocks;
   (void)sm_count;
@@ -313,7 +380,8 @@ bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
 }
 
 static int wgrad_tc_blocks(const WgTcParams& P, int sm_count) {
-  // enough K steps per CTA to amortise the partial write; at most one CTA per SM
+  // one CTA per SM while every CTA still gets at least two tiles (the partial write and the
+  // set-up are per CTA); the loader, not the MMA, bounds the per-tile time
   int nblk = P.n_tiles / 2;
   if (nblk > sm_count) nblk = sm_count;
   if (nblk < 1) nblk = 1;

@@ -92,13 +92,20 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     is_last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x < 4) {
+  if (is_last) {
+    // per-block partials summed in a fixed order: warp k (k < 4) owns sum k, lane j takes
+    // blocks j, j+32, ...
     __threadfence();
-    double s = 0;
-    for (unsigned blk = 0; blk < gridDim.x; ++blk)
-      s += *((volatile double*)&work->partial[(size_t)blk * 4 + threadIdx.x]);
-    sums[threadIdx.x] = s;
-    red[0][threadIdx.x] = s;
+    if (warp < 4) {
+      double s = 0;
+      for (unsigned blk = lane; blk < gridDim.x; blk += 32)
+        s += *((volatile double*)&work->partial[(size_t)blk * 4 + warp]);
+      s = warp_sum(s);
+      if (lane == 0) {
+        sums[warp] = s;
+        red[0][warp] = s;
+      }
+    }
   }
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
