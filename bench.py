@@ -226,6 +226,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line (some NCCL builds print their version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p,
                                                     float clip_norm, const float* __restrict__ lr,
                                                     float beta1, float beta2, float* __restrict__ state,
                                                     RedWork* __restrict__ work) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   if (MODE == 0 && denom) grad_scale /= (float)(*denom);
   const bool decay = MODE == 0 && l2_beta != 0.f;
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p,
                                                           float beta1,
                                                           float beta2, float eps,
                                                           const float* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
   if (denom) grad_scale /= (float)(*denom);
   const float lr_t = state[3];
   const float scale = state[4];
@@ -180,7 +184,7 @@ extern "C" int dincae_adam_step(float* params, const float* grads, float* m, flo
   int rc = cuda_rc(cudaMemsetAsync(workspace, 0, 16, st));
   if (rc) return rc;
   const int blocks = red_blocks(n);
-  sumsq_kernel<0><<<blocks, 256, 0, st>>>(params, grads, n, n_decay, l2_beta, grad_scale, denom,
+  launch_k(sumsq_kernel<0>, blocks, 256, 0, st, params, grads, n, n_decay, l2_beta, grad_scale, denom,
                                           clip_norm, lr, beta1, beta2, state,
                                           reinterpret_cast<RedWork*>(workspace));
   rc = check_launch();
@@ -188,7 +192,7 @@ extern "C" int dincae_adam_step(float* params, const float* grads, float* m, flo
   size_t ub = (n / 4 + 255) / 256;
   if (ub > 8 * 148) ub = 8 * 148;
   if (ub < 1) ub = 1;
-  adam_update_kernel<<<(unsigned)ub, 256, 0, st>>>(params, grads, m, v, n, n_decay, l2_beta,
+  launch_k(adam_update_kernel, (unsigned)ub, 256, 0, st, params, grads, m, v, n, n_decay, l2_beta,
                                                    grad_scale, denom, beta1, beta2, eps, state);
   return check_launch();
 }
@@ -200,7 +204,7 @@ extern "C" int dincae_l2_half_sumsq(const float* params, size_t n_decay, float* 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = cuda_rc(cudaMemsetAsync(workspace, 0, 16, st));
   if (rc) return rc;
-  sumsq_kernel<1><<<red_blocks(n_decay), 256, 0, st>>>(params, nullptr, n_decay, 0, 0.f, 1.f, nullptr,
+  launch_k(sumsq_kernel<1>, red_blocks(n_decay), 256, 0, st, params, nullptr, n_decay, 0, 0.f, 1.f, nullptr,
                                                        0.f, nullptr, 0.f, 0.f, out,
                                                        reinterpret_cast<RedWork*>(workspace));
   return check_launch();

@@ -14,6 +14,8 @@ __global__ void prepare_cube_kernel(const float* __restrict__ data,
                                     const uint8_t* __restrict__ missing, int T, size_t HW,
                                     double obs_var, int nomask, float* __restrict__ anom,
                                     double* __restrict__ meandata, uint8_t* __restrict__ never) {
+  pdl_trigger();
+  pdl_wait();
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   float sum = 0.f;
@@ -97,6 +99,8 @@ struct BatchParams {
 // One thread per (b, y, x).  All nvar channels of the pixel are produced plane by plane
 // (float4 stores, coalesced along x).
 __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int HW = P.H * P.W;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = gid < (long long)P.B * HW;
@@ -210,7 +214,7 @@ extern "C" int dincae_prepare_cube(const float* data, const uint8_t* missing, in
   const size_t HW = (size_t)H * W;
   const int threads = 128;
   const unsigned blocks = (unsigned)((HW + threads - 1) / threads);
-  prepare_cube_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+  launch_k(prepare_cube_kernel, blocks, threads, 0, (cudaStream_t)stream, 
       data, missing, T, HW, obs_var, nomask, anom, meandata, never);
   return check_launch();
 }
@@ -249,6 +253,6 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   const long long total = (long long)B * H * W;
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  build_batch_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(P);
+  launch_k(build_batch_kernel, blocks, threads, 0, (cudaStream_t)stream, P);
   return check_launch();
 }

@@ -27,6 +27,32 @@ inline int cuda_rc(cudaError_t e) {
   return DINCAE_OK;
 }
 
+// Programmatic dependent launch (experimental, DINCAE_PDL=1): every kernel of the library can
+// be launched with the programmatic-stream-serialization attribute; it raises
+// launch_dependents at its start and executes griddepcontrol.wait before its first global
+// access, so that the launch latency and the local prologue (barrier init, TMEM allocation,
+// shared-memory clears) of kernel N+1 overlap the tail of kernel N.  Without the attribute
+// the two instructions are no-ops.
+extern int g_use_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors: check_launch()
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

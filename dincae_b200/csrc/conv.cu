@@ -21,6 +21,8 @@ constexpr int CK = 4;    // logical input planes staged in shared memory per ste
 // free) and (b) the vertical pooling partner is lane^1.
 template <int TWQ, int TH, int MODE>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvParams P) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int TW = 4 * TWQ;
   constexpr int LW = TW + 2;           // loaded width (halo)
   constexpr int PW = LW | 1;           // odd pitch
@@ -220,6 +222,8 @@ struct WgradParams {
 constexpr int WG_TW = 16, WG_TH = 8, WG_PW = 19, WG_PH = 10;
 
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams P) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float4 smem[];
   float4* Us = smem;                                   // [cib][WG_PH][WG_PW]
   float4* Gs = smem + P.cib * WG_PH * WG_PW;           // [cob][WG_TH][WG_TW]
@@ -336,6 +340,8 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams P)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nblk,
                                                            int wsize, int cout_pad, int gp4,
                                                            float* __restrict__ dw, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = t >> 3, j = t & 7;
   const int total = wsize + cout_pad;
@@ -386,10 +392,10 @@ static int launch_conv(const ConvParams& P, cudaStream_t st) {
   const int groups = ceil_div(P.out_planes, CPB);
   if (P.W > 16) {
     dim3 grid(ceil_div(P.W, 32) * ceil_div(P.H, 8), groups, P.B);
-    conv3x3_kernel<8, 8, MODE><<<grid, 256, 0, st>>>(P);
+    launch_k(conv3x3_kernel<8, 8, MODE>, grid, 256, 0, st, P);
   } else {
     dim3 grid(ceil_div(P.W, 16) * ceil_div(P.H, 16), groups, P.B);
-    conv3x3_kernel<4, 16, MODE><<<grid, 256, 0, st>>>(P);
+    launch_k(conv3x3_kernel<4, 16, MODE>, grid, 256, 0, st, P);
   }
   return check_launch();
 }
@@ -514,7 +520,7 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
     if (rc < 0) return rc;
     if (rc == 0) {
       const int total = P.wsize + cout_pad;
-      wgrad_reduce_kernel<<<ceil_div(total * 8, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nb,
+      launch_k(wgrad_reduce_kernel, ceil_div(total * 8, 256), 256, 0, st, reinterpret_cast<float*>(workspace), nb,
                                                                P.wsize, cout_pad, gp * 4, dw, db);
       return check_launch();
     }
@@ -526,11 +532,11 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
   P.partial = reinterpret_cast<float*>(workspace);
   const size_t smem = ((size_t)P.cib * WG_PH * WG_PW + (size_t)P.cob * WG_TH * WG_TW) * sizeof(float4);
   dim3 grid(nblk, P.panels_ci * P.panels_co);
-  conv3x3_wgrad_kernel<<<grid, 256, smem, st>>>(P);
+  launch_k(conv3x3_wgrad_kernel, grid, 256, smem, st, P);
   rc = check_launch();
   if (rc) return rc;
   const int total = P.wsize + cout_pad;
-  wgrad_reduce_kernel<<<ceil_div(total * 8, 256), 256, 0, st>>>(P.partial, nblk, P.wsize, cout_pad,
+  launch_k(wgrad_reduce_kernel, ceil_div(total * 8, 256), 256, 0, st, P.partial, nblk, P.wsize, cout_pad,
                                                            gp * 4, dw, db);
   return check_launch();
 }

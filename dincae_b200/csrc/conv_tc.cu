@@ -141,9 +141,7 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
   int tc_k[3] = {0, 0, 0};
 #endif
 
-  if (MODE == 0 && tid < 64)
-    bias_s[tid] = (P.bias && tid < P.out_planes) ? __ldg(reinterpret_cast<const float4*>(P.bias) + tid)
-                                                 : f4_zero();
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], TC_LOAD_WARPS);
@@ -162,6 +160,12 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
                  :: "r"(smem_u32(&tmem_holder)), "r"(L.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // everything above is local to the CTA; from here on global memory written by the previous
+  // kernel is read (and buffers it may still be reading are written)
+  pdl_wait();
+  if (MODE == 0 && tid < 64)
+    bias_s[tid] = (P.bias && tid < P.out_planes) ? __ldg(reinterpret_cast<const float4*>(P.bias) + tid)
+                                                 : f4_zero();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -668,11 +672,11 @@ int launch_conv_tc(int mode, const ConvParams& P, cudaStream_t st) {
   }
   const int grid = Q.m.n_tiles < sm_count ? Q.m.n_tiles : sm_count;
   if (which == 0)
-    conv3x3_tc_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(Q, tm0, tm1);
+    launch_k(conv3x3_tc_kernel<0, 0>, grid, TC_THREADS, smem, st, Q, tm0, tm1);
   else if (which == 1)
-    conv3x3_tc_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(Q, tm0, tm1);
+    launch_k(conv3x3_tc_kernel<1, 0>, grid, TC_THREADS, smem, st, Q, tm0, tm1);
   else
-    conv3x3_tc_kernel<1, 1><<<grid, TC_THREADS, smem, st>>>(Q, tm0, tm1);
+    launch_k(conv3x3_tc_kernel<1, 1>, grid, TC_THREADS, smem, st, Q, tm0, tm1);
   return check_launch();
 }
 

@@ -27,7 +27,7 @@
 
 namespace dincae {
 
-constexpr int WG_LOAD_WARPS = 12;
+constexpr int WG_LOAD_WARPS = 20;
 constexpr int WG_MMA_WARP = WG_LOAD_WARPS;
 constexpr int WG_THREADS = 32 * (WG_LOAD_WARPS + 1);
 constexpr int WG_STAGES = 2;
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: zero the ring, ones row, item table, barriers, TMEM ------------------
+  pdl_trigger();
   for (int i = tid; i < (WG_STAGES * P.stage_floats) >> 2; i += WG_THREADS)
     reinterpret_cast<float4*>(ring)[i] = f4_zero();
   for (int i = tid; i < P.n_items; i += WG_THREADS) {
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
                  :: "r"(smem_u32(&tmem_holder)), "r"(P.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  pdl_wait();                 // the set-up above touches no global memory
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -417,9 +419,9 @@ int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, 
   }
   const size_t smem = (size_t)WG_STAGES * P.stage_floats * 4;
   if (gmode == 0)
-    conv3x3_wgrad_tc_kernel<0><<<nblk, WG_THREADS, smem, st>>>(P);
+    launch_k(conv3x3_wgrad_tc_kernel<0>, nblk, WG_THREADS, smem, st, P);
   else
-    conv3x3_wgrad_tc_kernel<1><<<nblk, WG_THREADS, smem, st>>>(P);
+    launch_k(conv3x3_wgrad_tc_kernel<1>, nblk, WG_THREADS, smem, st, P);
   *nblk_out = nblk;
   return check_launch();
 }

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ a,
                                                     const float* __restrict__ b, int ldb,
                                                     int M, int N, int K, int k_per_split,
                                                     float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float As[GK][GT + 4];
   __shared__ __align__(16) float Bs[GK][GT + 4];
   const int tid = threadIdx.x;
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ a,
 __global__ void splitk_epilogue_kernel(const float* __restrict__ part, int splits, int M, int N,
                                        const float* __restrict__ bias, int relu,
                                        const float* __restrict__ gate, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)M * N;
   if (e >= total) return;
@@ -100,6 +104,8 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ part, int split
 
 // db[n] = sum_b dz[b][n]
 __global__ void colsum_kernel(const float* __restrict__ dz, int B, int N, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -138,11 +144,11 @@ extern "C" int dincae_dense_fwd(const float* x, const float* w, const float* bia
   int kps = ceil_div(ceil_div(K, splits), GK) * GK;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, GT), ceil_div(B, GT), ceil_div(K, kps));
-  sgemm_kernel<0, 0><<<grid, 256, 0, st>>>(x, K, w, N, B, N, K, kps, (float*)workspace);
+  launch_k(sgemm_kernel<0, 0>, grid, 256, 0, st, x, K, w, N, B, N, K, kps, (float*)workspace);
   int rc = check_launch();
   if (rc) return rc;
   const size_t total = (size_t)B * N;
-  splitk_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  launch_k(splitk_epilogue_kernel, (unsigned)((total + 255) / 256), 256, 0, st, 
       (const float*)workspace, (int)grid.z, B, N, bias, relu, nullptr, y);
   return check_launch();
 }
@@ -157,11 +163,11 @@ extern "C" int dincae_dense_bwd_data(const float* dz, const float* w, const floa
   int kps = ceil_div(ceil_div(N, splits), GK) * GK;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(K, GT), ceil_div(B, GT), ceil_div(N, kps));
-  sgemm_kernel<0, 1><<<grid, 256, 0, st>>>(dz, N, w, N, B, K, N, kps, (float*)workspace);
+  launch_k(sgemm_kernel<0, 1>, grid, 256, 0, st, dz, N, w, N, B, K, N, kps, (float*)workspace);
   int rc = check_launch();
   if (rc) return rc;
   const size_t total = (size_t)B * K;
-  splitk_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  launch_k(splitk_epilogue_kernel, (unsigned)((total + 255) / 256), 256, 0, st, 
       (const float*)workspace, (int)grid.z, B, K, nullptr, 0, act_in, dx);
   return check_launch();
 }
@@ -172,9 +178,9 @@ extern "C" int dincae_dense_bwd_weight(const float* x, const float* dz, int B, i
   // dw[K,N] = x^T dz : M=K, N'=N, K'=B, A[m][k'] = x[k'][m]
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, GT), ceil_div(K, GT), 1);
-  sgemm_kernel<1, 0><<<grid, 256, 0, st>>>(x, K, dz, N, K, N, B, ceil_div(B, GK) * GK, dw);
+  launch_k(sgemm_kernel<1, 0>, grid, 256, 0, st, x, K, dz, N, K, N, B, ceil_div(B, GK) * GK, dw);
   int rc = check_launch();
   if (rc) return rc;
-  colsum_kernel<<<ceil_div(N, 128), 128, 0, st>>>(dz, B, N, db);
+  launch_k(colsum_kernel, ceil_div(N, 128), 128, 0, st, dz, B, N, db);
   return check_launch();
 }

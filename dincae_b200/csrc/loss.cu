@@ -19,6 +19,8 @@ __device__ __forceinline__ void head_eval(float a, float lb, float& m_rec, float
 __global__ void __launch_bounds__(256) head_recon_kernel(const float4* __restrict__ xrec, size_t n,
                                                          float* __restrict__ m_rec,
                                                          float* __restrict__ s2_rec) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 r = __ldg(&xrec[i]);
@@ -39,6 +41,8 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     int truth_uncertain, float neg_slope, const int32_t* __restrict__ n_noncloud,
     float4* __restrict__ g_out, double* __restrict__ sums, float* __restrict__ loss_out,
     LossWork* __restrict__ work, int round_tf32) {
+  pdl_trigger();
+  pdl_wait();
   const bool normalise = n_noncloud != nullptr;
   const float nn = normalise ? (float)(*n_noncloud) : 1.0f;
   const float inv_n = 1.0f / nn;
@@ -131,7 +135,7 @@ extern "C" int dincae_head_recon(const float* xrec, int B, int H, int W, float* 
                                  float* sigma2_rec, void* stream) {
   if (!xrec || !m_rec || !sigma2_rec || B <= 0 || H <= 0 || W <= 0) return DINCAE_EINVAL;
   const size_t n = (size_t)B * H * W;
-  head_recon_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(head_recon_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const float4*>(xrec), n, m_rec, sigma2_rec);
   return check_launch();
 }
@@ -153,7 +157,7 @@ extern "C" int dincae_head_loss(const float* xrec, const float* xtrue, int B, in
   cudaStream_t st = (cudaStream_t)stream;
   int rc = cuda_rc(cudaMemsetAsync(workspace, 0, 16, st));
   if (rc) return rc;
-  head_loss_kernel<<<loss_blocks(n), 256, 0, st>>>(
+  launch_k(head_loss_kernel, loss_blocks(n), 256, 0, st, 
       reinterpret_cast<const float4*>(xrec), reinterpret_cast<const float2*>(xtrue), n,
       truth_uncertain, neg_slope, n_noncloud, reinterpret_cast<float4*>(g_out), sums, loss_out,
       reinterpret_cast<LossWork*>(workspace), g_conv_backend == 1);
