@@ -40,7 +40,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ntime", type=int, default=5266)
@@ -309,7 +309,7 @@ def run_ours(a):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": workload_config(a, world), "clocks": clk, "e2e": e2e,
             "final_loss": losses[-1][0] if losses else None,
             "loss_first_last": [losses[0][0], e2e_losses[-1][0]] if losses and e2e_losses else None}
@@ -363,8 +363,16 @@ def run_ours(a):
         top = max(agg.items(), key=lambda kv: kv[1][0])
         peak, peak_src = peaks()
         ach = top[1][1] / (top[1][0] * 1e-3) / 1e9
+        # DRAM bytes of that kernel from the committed `ncu --set full` capture (profiles/),
+        # per launch; null when the capture holds another kernel
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.isfile(tp):
+            t = json.load(open(tp)).get(top[0])
+            if t:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "kernel": top[0],
+                            "frac": ach / peak, "traffic": traffic, "kernel": top[0],
                             "kernel_ms": top[1][0], "kernel_share_of_step": top[1][0] / total_ms,
                             "algorithmic_bytes": top[1][1], "algorithmic_flops": top[1][2],
                             "peak_source": peak_src,

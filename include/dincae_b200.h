@@ -89,10 +89,18 @@ int dincae_build_batch(const float* anom, const uint8_t* missing,
 
 /* ---- 3x3 convolutions -------------------------------------------------------------- */
 
-/* Which kernels dincae_conv3x3_fwd / dincae_conv3x3_dgrad launch: 1 (default) = tcgen05
- * kind::tf32 implicit GEMM with TMEM accumulators (operands rounded to TF32, fp32 accumulate),
- * 0 = fp32 FFMA kernels (bit-for-bit fp32 arithmetic; also taken automatically for shapes the
- * tensor-core path does not cover).  Process-wide setting. */
+/* Which kernels dincae_conv3x3_fwd / _dgrad / _wgrad launch: 1 (default) = tcgen05 kind::tf32
+ * implicit GEMMs with TMEM accumulators and TMA loads (fp32 accumulate), 0 = fp32 FFMA kernels
+ * (bit-for-bit fp32 arithmetic; also taken automatically for shapes the tensor-core path does
+ * not cover).  Process-wide setting.
+ * TF32 contract of back end 1: the tensor cores ignore the low 13 mantissa bits of an
+ * operand.  Data staged through registers is rounded (nearest, ties away) by the kernels;
+ * conv sources stored at the conv's own resolution are fetched by TMA untouched and must
+ * therefore already be TF32-representable.  Every producer in this library rounds on store
+ * while back end 1 is selected: the outputs of conv3x3_fwd / conv3x3_dgrad (both kernel
+ * families), `xin` of dincae_build_batch (xtrue stays exact) and `g_out` of dincae_head_loss.
+ * A caller feeding its own tensors should round them the same way (other values are
+ * truncated, not rejected). */
 int dincae_set_conv_backend(int backend);
 int dincae_get_conv_backend(void);
 
