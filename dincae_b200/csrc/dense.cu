@@ -85,6 +85,129 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ a,
   }
 }
 
+// Vectorised variant used when every row pitch and pointer is 16-byte aligned (always the case
+// for the padded dense layers): float4 global loads along the contiguous dimension, the next
+// K tile prefetched into registers while the current one is multiplied, and optional fused
+// work so that the skinny GEMMs of the bottleneck need no follow-up kernels:
+//   EPI 0: raw partial of a K split -> out[split][M][N]
+//   EPI 1: y = epi(acc + bias) with ReLU / gate (single split)
+//   colsum != null and blockIdx.y == 0: colsum[n] = sum over k of Bm[k][n]  (bias gradient
+//   of the weight-gradient GEMM, whose B operand is dz)
+constexpr int VK = 32;
+template <int TA, int TB, int EPI>
+__global__ void __launch_bounds__(256) sgemm_v4_kernel(const float* __restrict__ a, int lda,
+                                                       const float* __restrict__ b, int ldb,
+                                                       int M, int N, int K, int k_per_split,
+                                                       float* __restrict__ out,
+                                                       const float* __restrict__ bias, int relu,
+                                                       const float* __restrict__ gate,
+                                                       float* __restrict__ colsum) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float As[VK][GT + 4];
+  __shared__ __align__(16) float Bs[VK][GT + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;                         // column tid (< GT) of the B tile, summed over k
+  const bool want_cs = colsum != nullptr && blockIdx.y == 0;
+
+  float4 ra[2], rb[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = tid + 256 * r;
+      if (TA == 0) {                          // a[m][k], float4 along k
+        const int m = f >> 3, k = k0 + 4 * (f & 7);
+        ra[r] = (m0 + m < M && k < kend) ? __ldg(reinterpret_cast<const float4*>(a + (size_t)(m0 + m) * lda + k))
+                                         : f4_zero();
+      } else {                                // a[k][m], float4 along m
+        const int k = k0 + (f >> 4), m = m0 + 4 * (f & 15);
+        ra[r] = (m < M && k < kend) ? __ldg(reinterpret_cast<const float4*>(a + (size_t)k * lda + m))
+                                    : f4_zero();
+      }
+      if (TB == 0) {                          // b[k][n], float4 along n
+        const int k = k0 + (f >> 4), n = n0 + 4 * (f & 15);
+        rb[r] = (n < N && k < kend) ? __ldg(reinterpret_cast<const float4*>(b + (size_t)k * ldb + n))
+                                    : f4_zero();
+      } else {                                // b[n][k], float4 along k
+        const int n = f >> 3, k = k0 + 4 * (f & 7);
+        rb[r] = (n0 + n < N && k < kend) ? __ldg(reinterpret_cast<const float4*>(b + (size_t)(n0 + n) * ldb + k))
+                                         : f4_zero();
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = tid + 256 * r;
+      if (TA == 0) {
+        const int m = f >> 3, k = 4 * (f & 7);
+        As[k][m] = ra[r].x; As[k + 1][m] = ra[r].y; As[k + 2][m] = ra[r].z; As[k + 3][m] = ra[r].w;
+      } else {
+        *reinterpret_cast<float4*>(&As[f >> 4][4 * (f & 15)]) = ra[r];
+      }
+      if (TB == 0) {
+        *reinterpret_cast<float4*>(&Bs[f >> 4][4 * (f & 15)]) = rb[r];
+      } else {
+        const int n = f >> 3, k = 4 * (f & 7);
+        Bs[k][n] = rb[r].x; Bs[k + 1][n] = rb[r].y; Bs[k + 2][n] = rb[r].z; Bs[k + 3][n] = rb[r].w;
+      }
+    }
+  };
+
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += VK) {
+    stash();
+    __syncthreads();
+    if (k0 + VK < kend) fetch(k0 + VK);
+#pragma unroll
+    for (int k = 0; k < VK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][tm]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    if (want_cs && tid < GT) {
+#pragma unroll
+      for (int k = 0; k < VK; ++k) csum += Bs[k][tid];
+    }
+    __syncthreads();
+  }
+  if (want_cs && tid < GT && n0 + tid < N) colsum[n0 + tid] = csum;
+  float* o = EPI == 0 ? out + (size_t)blockIdx.z * M * N : out;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + tm + i;
+    if (gm >= M) continue;
+    const int gn = n0 + tn;
+    if (gn >= N) continue;                       // N is a multiple of 4: the float4 is in or out
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (EPI == 1) {
+      if (bias) v = f4_add(v, __ldg(reinterpret_cast<const float4*>(bias + gn)));
+      if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+      if (gate) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)gm * N + gn));
+        v = make_float4(g.x > 0.f ? v.x : 0.f, g.y > 0.f ? v.y : 0.f, g.z > 0.f ? v.z : 0.f, g.w > 0.f ? v.w : 0.f);
+      }
+    }
+    *reinterpret_cast<float4*>(o + (size_t)gm * N + gn) = v;
+  }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 // y[m][n] = epi(sum_s part[s][m][n] + bias[n]);  epi: relu and/or multiply by (gate > 0).
 __global__ void splitk_epilogue_kernel(const float* __restrict__ part, int splits, int M, int N,
                                        const float* __restrict__ bias, int relu,
@@ -115,7 +238,8 @@ __global__ void colsum_kernel(const float* __restrict__ dz, int B, int N, float*
 
 static int pick_splits(int M, int N, int K) {
   const int tiles = ceil_div(M, GT) * ceil_div(N, GT);
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (tiles >= 120) return 1;                // enough CTAs: keep the epilogue fused
+  int splits = (148 + tiles - 1) / tiles;
   const int max_splits = ceil_div(K, 4 * GK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -141,10 +265,21 @@ extern "C" int dincae_dense_fwd(const float* x, const float* w, const float* bia
   if (!x || !w || !y || !workspace || B <= 0 || K <= 0 || N <= 0) return DINCAE_EINVAL;
   const int splits = pick_splits(B, N, K);
   if ((size_t)splits * B * N * sizeof(float) > workspace_bytes) return DINCAE_ENOSPC;
-  int kps = ceil_div(ceil_div(K, splits), GK) * GK;
+  int kps = ceil_div(ceil_div(K, splits), VK) * VK;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, GT), ceil_div(B, GT), ceil_div(K, kps));
-  launch_k(sgemm_kernel<0, 0>, grid, 256, 0, st, x, K, w, N, B, N, K, kps, (float*)workspace);
+  const bool vec = !(K & 3) && !(N & 3) && aligned16(x) && aligned16(w) && aligned16(y) &&
+                   aligned16(workspace) && (!bias || aligned16(bias));
+  if (vec && grid.z == 1) {
+    launch_k(sgemm_v4_kernel<0, 0, 1>, grid, 256, 0, st, x, K, w, N, B, N, K, kps, y, bias, relu,
+             (const float*)nullptr, (float*)nullptr);
+    return check_launch();
+  }
+  if (vec)
+    launch_k(sgemm_v4_kernel<0, 0, 0>, grid, 256, 0, st, x, K, w, N, B, N, K, kps, (float*)workspace,
+             (const float*)nullptr, 0, (const float*)nullptr, (float*)nullptr);
+  else
+    launch_k(sgemm_kernel<0, 0>, grid, 256, 0, st, x, K, w, N, B, N, K, kps, (float*)workspace);
   int rc = check_launch();
   if (rc) return rc;
   const size_t total = (size_t)B * N;
@@ -160,10 +295,21 @@ extern "C" int dincae_dense_bwd_data(const float* dz, const float* w, const floa
   // dx[B,K] = dz[B,N] * w^T : GEMM with M=B, N'=K, K'=N, Bm[k'][n'] = w[n'][k']
   const int splits = pick_splits(B, K, N);
   if ((size_t)splits * B * K * sizeof(float) > workspace_bytes) return DINCAE_ENOSPC;
-  int kps = ceil_div(ceil_div(N, splits), GK) * GK;
+  int kps = ceil_div(ceil_div(N, splits), VK) * VK;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(K, GT), ceil_div(B, GT), ceil_div(N, kps));
-  launch_k(sgemm_kernel<0, 1>, grid, 256, 0, st, dz, N, w, N, B, K, N, kps, (float*)workspace);
+  const bool vec = !(K & 3) && !(N & 3) && aligned16(dz) && aligned16(w) && aligned16(dx) &&
+                   aligned16(workspace) && (!act_in || aligned16(act_in));
+  if (vec && grid.z == 1) {
+    launch_k(sgemm_v4_kernel<0, 1, 1>, grid, 256, 0, st, dz, N, w, N, B, K, N, kps, dx,
+             (const float*)nullptr, 0, act_in, (float*)nullptr);
+    return check_launch();
+  }
+  if (vec)
+    launch_k(sgemm_v4_kernel<0, 1, 0>, grid, 256, 0, st, dz, N, w, N, B, K, N, kps, (float*)workspace,
+             (const float*)nullptr, 0, (const float*)nullptr, (float*)nullptr);
+  else
+    launch_k(sgemm_kernel<0, 1>, grid, 256, 0, st, dz, N, w, N, B, K, N, kps, (float*)workspace);
   int rc = check_launch();
   if (rc) return rc;
   const size_t total = (size_t)B * K;
@@ -178,6 +324,12 @@ extern "C" int dincae_dense_bwd_weight(const float* x, const float* dz, int B, i
   // dw[K,N] = x^T dz : M=K, N'=N, K'=B, A[m][k'] = x[k'][m]
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, GT), ceil_div(K, GT), 1);
+  if (!(K & 3) && !(N & 3) && aligned16(x) && aligned16(dz) && aligned16(dw)) {
+    // weight gradient with the bias gradient (column sums of dz) fused into the first row of CTAs
+    launch_k(sgemm_v4_kernel<1, 0, 1>, grid, 256, 0, st, x, K, dz, N, K, N, B, ceil_div(B, VK) * VK, dw,
+             (const float*)nullptr, 0, (const float*)nullptr, db);
+    return check_launch();
+  }
   launch_k(sgemm_kernel<1, 0>, grid, 256, 0, st, x, K, dz, N, K, N, B, ceil_div(B, GK) * GK, dw);
   int rc = check_launch();
   if (rc) return rc;
