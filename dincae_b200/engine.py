@@ -232,9 +232,29 @@ class Network:
                     h, w = self._conv_res(e)
                     ws.append(self.lib.dincae_conv3x3_wgrad_workspace(e["cinp"], 0, e["cout_pad"], B, h, w))
         self.workspace = torch.zeros(max(ws + [256]), dtype=torch.uint8, device=dev)
+        # Weight gradients run on a side stream next to the data-gradient chain (they only
+        # share inputs), with their own scratch so the two streams never touch the same bytes.
+        import os
+        self._side_parts = int(os.environ.get("DINCAE_SIDE_PARTS", "7"))
+        self.side = torch.cuda.Stream(device=dev) if (train and os.environ.get("DINCAE_NO_SIDE_STREAM") != "1") else None
+        self.workspace_side = torch.zeros_like(self.workspace) if train else None
         self._ent = {e["name"]: e for e in P.entries}
         self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
         self.tracer = None       # optional callable(label, fn, args, alg_bytes, alg_flops)
+
+    def _fork(self, fn, part=1):
+        """Run ``fn`` (which enqueues kernels) on the side stream, after everything enqueued so
+        far on the current stream; joined again by ``_join`` (works inside graph capture)."""
+        if self.side is None or not (self._side_parts & part):
+            fn()
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            fn()
+
+    def _join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
     def _call(self, label, fname, args, alg_bytes=0, alg_flops=0):
         """Enqueue one C-ABI call.  ``alg_bytes`` / ``alg_flops`` are the ALGORITHMIC traffic
@@ -329,6 +349,7 @@ class Network:
         P, lib, st = self.plan, self.lib, stream_ptr()
         L = P.L
         wsp, wsn = ptr(self.workspace), self.workspace.numel()
+        wss = ptr(self.workspace_side)
         self._call("head_loss", "dincae_head_loss", (
             ptr(self.D[L]), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
             ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self.loss_sums),
@@ -344,11 +365,11 @@ class Network:
             hh, wh = P.sizes[r + 1]
             co = P.dec_c[l]
             nb = 4 * B * (hh * wh * up + h * w * (sk + co)) + 36 * (up + sk) * co
-            self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad", (
+            self._fork(lambda: self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.D[l - 1]), c0p, 1, ptr(self.X[r]) if sk else None, c1p,
                 ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l], e["cout_pad"], B, h, w,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                wsp, wsn, st), nb, 18 * (up + sk) * co * B * h * w)
+                wss, wsn, stream_ptr()), nb, 18 * (up + sk) * co * B * h * w), 1)
             prev_slope = NEG_SLOPE if l > 1 else (0.0 if has_dense else 1.0)
             want_skip = bool(sk) and r >= 1
             cin_eff = up + (sk if want_skip else 0)
@@ -364,10 +385,10 @@ class Network:
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
-            self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
+            self._fork(lambda: self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
                 ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                st), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn)
+                stream_ptr()), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn), 2)
             dst = self.dZ[i] if i > 0 else self.dX[L].view(self.Bmax, -1)
             self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
                 ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
@@ -382,11 +403,11 @@ class Network:
             ci, co = P.enc_c[l - 1], P.enc_c[l]
             hh, wh = P.sizes[l]
             nb = 4 * B * (h * w * ci + hh * wh * co) + B * h * w * co // 8 + 36 * ci * co
-            self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad", (
+            self._fork(lambda: self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
                 None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l], e["cout_pad"], B, h, w,
                 ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                wsp, wsn, st), nb, 18 * ci * co * B * h * w)
+                wss, wsn, stream_ptr()), nb, 18 * ci * co * B * h * w), 4)
             if l > 1:
                 has_add = self.dXskip[l - 1] is not None
                 nb = 4 * B * (hh * wh * co + h * w * ci * (2 if has_add else 1)) + B * h * w * co // 8 + 36 * ci * co
@@ -397,6 +418,7 @@ class Network:
                     P.ep[l - 1], ptr(self.dX[l - 1]),
                     ptr(self.dXskip[l - 1]) if has_add else None, st),
                     nb, 18 * ci * co * B * h * w)
+        self._join()
 
     def l2_value(self):
         """0.5 * sum of squares of all kernels -> self.l2_out (device)."""

@@ -41,7 +41,11 @@ class Trainer:
         dev = cube.dev
         B = self.B
         # [frame(B) | cloud(B) | seq int64 (2B int32)]
-        self.idx_host = torch.zeros(4 * B, dtype=torch.int32).pin_memory()
+        # pinned staging ring for the per-step indices: the host runs ahead of the stream, so a
+        # slot may only be rewritten once the asynchronous copy that read it has executed
+        self._idx_ring = [torch.zeros(4 * B, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self._idx_events = [None] * len(self._idx_ring)
+        self._idx_pos = 0
         self.idx_dev = torch.zeros(4 * B, dtype=torch.int32, device=dev)
         self.frame_idx = self.idx_dev[:B]
         self.cloud_idx = self.idx_dev[B:2 * B]
@@ -107,11 +111,18 @@ class Trainer:
 
     def upload_indices(self, frame_idx, cloud_idx, seq):
         B = self.B
-        h = self.idx_host
+        slot = self._idx_pos % len(self._idx_ring)
+        self._idx_pos += 1
+        if self._idx_events[slot] is not None:
+            self._idx_events[slot].synchronize()
+        h = self._idx_ring[slot]
         h[:B] = torch.from_numpy(np.ascontiguousarray(frame_idx, dtype=np.int32))
         h[B:2 * B] = torch.from_numpy(np.ascontiguousarray(cloud_idx, dtype=np.int32))
         h[2 * B:].view(torch.int64)[:] = torch.from_numpy(np.ascontiguousarray(seq, dtype=np.int64))
         self.idx_dev.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._idx_events[slot] = ev
 
     def train_step(self, frame_idx, cloud_idx, seq):
         """Enqueue one step for this rank's B frames; the loss is fetched lazily."""
@@ -170,7 +181,9 @@ class Reconstructor:
         self.py_random = py_random
         dev = cube.dev
         B = self.B
-        self.idx_host = torch.zeros(4 * B, dtype=torch.int32).pin_memory()
+        self._idx_ring = [torch.zeros(4 * B, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self._idx_events = [None] * len(self._idx_ring)
+        self._idx_pos = 0
         self.idx_dev = torch.zeros(4 * B, dtype=torch.int32, device=dev)
         self.out_host = [torch.zeros(2, B, plan.H, plan.W).pin_memory() for _ in range(2)]
         self.out_dev = torch.zeros(2, B, plan.H, plan.W, device=dev)
@@ -192,7 +205,11 @@ class Reconstructor:
         """frames: int array (n <= B).  Returns pinned host tensor [2,B,H,W] (valid after a
         stream sync): [0] = m_rec, [1] = sigma2_rec."""
         n, B = len(frames), self.B
-        h = self.idx_host
+        islot = self._idx_pos % len(self._idx_ring)
+        self._idx_pos += 1
+        if self._idx_events[islot] is not None:
+            self._idx_events[islot].synchronize()      # the copy that read this slot has run
+        h = self._idx_ring[islot]
         h[:n] = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.int32))
         if self.train_mode_inputs:
             import random as _r
@@ -203,6 +220,9 @@ class Reconstructor:
             h[2 * B:].view(torch.int64)[:n] = seq
             self._seq += n
         self.idx_dev.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._idx_events[islot] = ev
         if self.use_graph:
             g = self._graphs.get(n)
             if g is None:
