@@ -89,9 +89,18 @@ class Plan:
         for l in range(1, self.L + 1):
             up, sk, _ = self.dec_sources(l)
             conv(cname(), [up] + ([sk] if sk else []), self.dec_c[l])
-        # flat layout: all kernels first (they receive the L2 term), then all biases
+        # flat layout: all kernels first (they receive the L2 term), then all biases.  Among the
+        # kernels, those whose gradient is final first in the backward pass (dense + decoder)
+        # come first, so that the data-parallel trainer all-reduces ONE contiguous big bucket
+        # while the encoder backward still runs, and one contiguous rest bucket afterwards.
         off = 0
-        for e in ent:
+        n_enc = 2 * self.L
+        for e in ent[n_enc:]:
+            if e["kind"].endswith("_w"):
+                e["offset"] = off
+                off = layout.round_up(off + e["size"], 64)
+        self.n_early = off
+        for e in ent[:n_enc]:
             if e["kind"].endswith("_w"):
                 e["offset"] = off
                 off = layout.round_up(off + e["size"], 64)
@@ -344,12 +353,27 @@ class Network:
             16 * B * P.H * P.W, 0)
 
     # ---- loss + backward --------------------------------------------------------------------
-    def loss_backward(self, B, truth_uncertain=False, normalise=True):
-        """head + NLL, then gradients of every parameter into self.grads."""
+    def grad_buckets(self):
+        """(start, end) ranges of the flat gradient buffer in the order they become final
+        during ``loss_backward``: [dense + decoder kernels] after phase 1 (97 % of the bytes at
+        config A), then [encoder kernels + all biases] after phase 2."""
+        return (0, self.plan.n_early), (self.plan.n_early, self.plan.n_params_flat)
+
+    def loss_backward(self, B, truth_uncertain=False, normalise=True, phase=0):
+        """head + NLL, then gradients of every parameter into self.grads.
+        phase 1 = loss head, decoder and dense backward; phase 2 = encoder backward; 0 = both
+        (the data-parallel trainer all-reduces the phase-1 gradients while phase 2 runs)."""
+        if phase == 0:
+            self.loss_backward(B, truth_uncertain, normalise, 1)
+            self.loss_backward(B, truth_uncertain, normalise, 2)
+            return
         P, lib, st = self.plan, self.lib, stream_ptr()
         L = P.L
         wsp, wsn = ptr(self.workspace), self.workspace.numel()
         wss = ptr(self.workspace_side)
+        has_dense = len(P.dense_units) > 0
+        if phase == 2:
+            return self._backward_encoder(B, has_dense, wss, wsn, st)
         self._call("head_loss", "dincae_head_loss", (
             ptr(self.D[L]), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
             ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self.loss_sums),
@@ -394,6 +418,10 @@ class Network:
                 ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
                 ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
                 4 * (B * nn + kk * nn + B * kk), 2 * B * kk * nn)
+        self._join()
+
+    def _backward_encoder(self, B, has_dense, wss, wsn, st):
+        P, L = self.plan, self.plan.L
         top_grad = self.dX[L] if has_dense else self.GD[0]
         for l in range(L, 0, -1):
             h, w = P.sizes[l - 1]

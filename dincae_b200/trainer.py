@@ -60,16 +60,19 @@ class Trainer:
         self.launches_per_step = None
 
     # ---- one optimisation step ---------------------------------------------------------------
-    def _enqueue_fwd_bwd(self):
+    def _enqueue_fwd_bwd(self, phases=(1, 2)):
         net, B = self.net, self.B
-        net.n_noncloud.zero_()
-        self.cube.build_batch(self.frame_idx, self.cloud_idx, B, net.X[0], net.xtrue,
-                              net.n_noncloud, jitter_std=self.jitter_std, seed=self.noise_seed,
-                              noise_seq=self.noise_seq)
-        net.forward(B)
-        net.loss_backward(B, self.truth_uncertain, normalise=False)
-        if self.l2_beta != 0.0:
-            net.l2_value()
+        if 1 in phases:
+            net.n_noncloud.zero_()
+            self.cube.build_batch(self.frame_idx, self.cloud_idx, B, net.X[0], net.xtrue,
+                                  net.n_noncloud, jitter_std=self.jitter_std, seed=self.noise_seed,
+                                  noise_seq=self.noise_seq)
+            net.forward(B)
+            net.loss_backward(B, self.truth_uncertain, normalise=False, phase=1)
+        if 2 in phases:
+            net.loss_backward(B, self.truth_uncertain, normalise=False, phase=2)
+            if self.l2_beta != 0.0:
+                net.l2_value()
 
     def _enqueue_update(self):
         net = self.net
@@ -134,9 +137,18 @@ class Trainer:
         if self.dist is None:
             self._run("step", lambda: (self._enqueue_fwd_bwd(), self._enqueue_update()))
         else:
-            self._run("fwd_bwd", self._enqueue_fwd_bwd)
-            self.dist.all_reduce(self.net.grads, group=self.group)
-            self.dist.all_reduce(self.net.loss_sums, group=self.group)
+            # gradients become final in two phases; the big bucket (dense + decoder kernels)
+            # is all-reduced on NCCL's stream while the encoder backward still runs
+            big, rest = self.net.grad_buckets()
+            g = self.net.grads
+            self._run("fwd_bwd1", lambda: self._enqueue_fwd_bwd((1,)))
+            h_big = self.dist.all_reduce(g[big[0]:big[1]], group=self.group, async_op=True)
+            self._run("bwd2", lambda: self._enqueue_fwd_bwd((2,)))
+            hs = [self.dist.all_reduce(g[rest[0]:rest[1]], group=self.group, async_op=True),
+                  self.dist.all_reduce(self.net.loss_sums, group=self.group, async_op=True)]
+            h_big.wait()
+            for h in hs:
+                h.wait()
             self._run("update", self._enqueue_update)
         # loss bookkeeping: 4 sums + L2 value -> pinned ring (async)
         slot = self._ring_pos % self._ring.shape[0]
