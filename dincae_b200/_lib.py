@@ -47,6 +47,8 @@ SIGNATURES = {
     "dincae_adam_step": (c_int, [vp, vp, vp, vp, c_size_t, c_size_t, c_float, c_float, vp, c_float,
                                  c_float, c_float, c_float, vp, vp, vp, c_size_t, vp]),
     "dincae_l2_half_sumsq": (c_int, [vp, c_size_t, vp, vp, c_size_t, vp]),
+    "dincae_ensemble_accumulate": (c_int, [vp, vp, c_float, c_size_t, vp, vp, vp]),
+    "dincae_ensemble_finalize": (c_int, [vp, vp, c_size_t, c_int, c_float, vp, vp, vp]),
 }
 
 

@@ -210,6 +210,20 @@ int dincae_adam_step(float* params, const float* grads, float* m, float* v,
 int dincae_l2_half_sumsq(const float* params, size_t n_decay, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- ensemble averaging of saved reconstructions ------------------------------------- */
+
+/* The reference's README (README.md:90) recommends averaging the reconstructions saved every
+ * `save_each` epochs (DINCAE/__init__.py:671-689 writes them); it ships no code for it.
+ * accumulate: add one member (mean_rec, sigma_rec: n floats each, `fill` marks masked
+ *   entries, which are skipped) into acc[3][n] doubles = (sum m, sum sigma^2, sum m^2) and
+ *   count[n] (both zero-initialised by the caller).
+ * finalize: mean_out = sum m / count; sigma_out = sqrt(mean sigma^2) (mixture == 0) or
+ *   sqrt(mean sigma^2 + variance of the member means) (mixture != 0); `fill` where count == 0. */
+int dincae_ensemble_accumulate(const float* mean_rec, const float* sigma_rec, float fill, size_t n,
+                               double* acc, int32_t* count, void* stream);
+int dincae_ensemble_finalize(const double* acc, const int32_t* count, size_t n, int mixture,
+                             float fill, float* mean_out, float* sigma_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,18 @@ def test_product_never_imports_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(root, d, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_ensemble_oracle_definitions():
+    """numpy oracle of the ensemble averaging: masked members are skipped; 'mixture' adds the
+    spread of the member means (law of total variance)."""
+    from oracle import ensemble_np
+    m1 = np.ma.masked_array(np.array([1.0, 2.0, 5.0], dtype="f4"), [False, False, True])
+    m2 = np.ma.masked_array(np.array([3.0, 2.0, 7.0], dtype="f4"), [False, True, True])
+    s1 = np.ma.masked_array(np.array([1.0, 2.0, 1.0], dtype="f4"), [False, False, True])
+    s2 = np.ma.masked_array(np.array([1.0, 4.0, 1.0], dtype="f4"), [False, True, True])
+    mu, sg = ensemble_np.average([m1, m2], [s1, s2], "mean_var")
+    assert np.allclose(np.ma.getdata(mu)[:2], [2.0, 2.0]) and np.ma.getmaskarray(mu)[2]
+    assert np.allclose(np.ma.getdata(sg)[:2], [1.0, 2.0])
+    mu, sg = ensemble_np.average([m1, m2], [s1, s2], "mixture")
+    assert np.allclose(np.ma.getdata(sg)[:2], [np.sqrt(1.0 + 1.0), 2.0])
