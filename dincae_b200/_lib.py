@@ -35,6 +35,9 @@ SIGNATURES = {
     "dincae_conv3x3_wgrad_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "dincae_conv3x3_wgrad": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
                                      c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]),
+    "dincae_conv3x3_wgrad_partial": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
+                                             c_int, c_int, c_int, c_int, vp, c_size_t, POINTER(c_int), vp]),
+    "dincae_conv3x3_wgrad_reduce": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp, vp]),
     "dincae_dense_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_dense_fwd": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),

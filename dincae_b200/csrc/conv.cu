@@ -498,12 +498,12 @@ extern "C" size_t dincae_conv3x3_wgrad_workspace(int c0p, int c1p, int cout_pad,
   return align_up(worst, 256);
 }
 
-extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, const float* src1,
-                                    int c1p, const float* g_full, const float* g_pool,
-                                    const uint16_t* sign, float neg_slope, int gp, int cout_pad,
-                                    int B, int H, int W, float* dw, float* db, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
-  if (!src0 || !dw || !db || !workspace || c0p <= 0 || gp <= 0 || B <= 0 || H <= 0 || W <= 0)
+extern "C" int dincae_conv3x3_wgrad_partial(const float* src0, int c0p, int src0_half, const float* src1,
+                                            int c1p, const float* g_full, const float* g_pool,
+                                            const uint16_t* sign, float neg_slope, int gp, int cout_pad,
+                                            int B, int H, int W, void* workspace, size_t workspace_bytes,
+                                            int* n_partials, void* stream) {
+  if (!src0 || !workspace || !n_partials || c0p <= 0 || gp <= 0 || B <= 0 || H <= 0 || W <= 0)
     return DINCAE_EINVAL;
   if (gp * 4 > cout_pad || (cout_pad & 3)) return DINCAE_EINVAL;
   WgradParams P = {};
@@ -519,10 +519,8 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
                   workspace_bytes, &nb, st);
     if (rc < 0) return rc;
     if (rc == 0) {
-      const int total = P.wsize + cout_pad;
-      launch_k(wgrad_reduce_kernel, ceil_div(total * 8, 256), 256, 0, st, reinterpret_cast<float*>(workspace), nb,
-                                                               P.wsize, cout_pad, gp * 4, dw, db);
-      return check_launch();
+      *n_partials = nb;
+      return DINCAE_OK;
     }
   }
   int nblk;
@@ -533,10 +531,30 @@ extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, c
   const size_t smem = ((size_t)P.cib * WG_PH * WG_PW + (size_t)P.cob * WG_TH * WG_TW) * sizeof(float4);
   dim3 grid(nblk, P.panels_ci * P.panels_co);
   launch_k(conv3x3_wgrad_kernel, grid, 256, smem, st, P);
-  rc = check_launch();
-  if (rc) return rc;
-  const int total = P.wsize + cout_pad;
-  launch_k(wgrad_reduce_kernel, ceil_div(total * 8, 256), 256, 0, st, P.partial, nblk, P.wsize, cout_pad,
-                                                           gp * 4, dw, db);
+  *n_partials = nblk;
   return check_launch();
+}
+
+extern "C" int dincae_conv3x3_wgrad_reduce(const void* workspace, int n_partials, int cinp, int gp,
+                                           int cout_pad, float* dw, float* db, void* stream) {
+  if (!workspace || !dw || !db || n_partials <= 0 || cinp <= 0 || gp <= 0 || gp * 4 > cout_pad)
+    return DINCAE_EINVAL;
+  const int wsize = 9 * cinp * cout_pad * 4;
+  const int total = wsize + cout_pad;
+  launch_k(wgrad_reduce_kernel, ceil_div(total * 8, 256), 256, 0, (cudaStream_t)stream,
+           reinterpret_cast<const float*>(workspace), n_partials, wsize, cout_pad, gp * 4, dw, db);
+  return check_launch();
+}
+
+extern "C" int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half, const float* src1,
+                                    int c1p, const float* g_full, const float* g_pool,
+                                    const uint16_t* sign, float neg_slope, int gp, int cout_pad,
+                                    int B, int H, int W, float* dw, float* db, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!dw || !db) return DINCAE_EINVAL;
+  int nb = 0;
+  int rc = dincae_conv3x3_wgrad_partial(src0, c0p, src0_half, src1, c1p, g_full, g_pool, sign, neg_slope, gp,
+                                        cout_pad, B, H, W, workspace, workspace_bytes, &nb, stream);
+  if (rc) return rc;
+  return dincae_conv3x3_wgrad_reduce(workspace, nb, c0p + (src1 ? c1p : 0), gp, cout_pad, dw, db, stream);
 }

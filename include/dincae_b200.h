@@ -210,6 +210,18 @@ int dincae_adam_step(float* params, const float* grads, float* m, float* v,
 int dincae_l2_half_sumsq(const float* params, size_t n_decay, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* dincae_conv3x3_wgrad in two steps, for callers that overlap the (small) reduction of one
+ * layer with the main kernel of the next on another stream: `_partial` writes *n_partials
+ * (host int, known when the call returns) partial gradients into `workspace`; `_reduce` sums
+ * them in a fixed order into dw / db.  Same arguments and layouts as dincae_conv3x3_wgrad;
+ * cinp = c0p + c1p. */
+int dincae_conv3x3_wgrad_partial(const float* src0, int c0p, int src0_half, const float* src1, int c1p,
+                                 const float* g_full, const float* g_pool, const uint16_t* sign,
+                                 float neg_slope, int gp, int cout_pad, int B, int H, int W,
+                                 void* workspace, size_t workspace_bytes, int* n_partials, void* stream);
+int dincae_conv3x3_wgrad_reduce(const void* workspace, int n_partials, int cinp, int gp, int cout_pad,
+                                float* dw, float* db, void* stream);
+
 /* ---- ensemble averaging of saved reconstructions ------------------------------------- */
 
 /* The reference's README (README.md:90) recommends averaging the reconstructions saved every

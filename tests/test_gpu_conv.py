@@ -215,6 +215,34 @@ def test_relu_bottleneck_slope_and_no_prev_act(backend):
         assert rel_err(from_p4(g_prev, C0), want.numpy()) < TOL
 
 
+def test_wgrad_in_two_steps_equals_the_fused_call(backend):
+    """dincae_conv3x3_wgrad_partial + _reduce (for callers that put the reduction on another
+    stream) give bit-identical dw / db to dincae_conv3x3_wgrad."""
+    import ctypes
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(9)
+    B, H, W, Cin, Cout = 3, 20, 24, 10, 16
+    x = feed(torch.randn(B, H, W, Cin, generator=g), backend)
+    G = feed(torch.randn(B, H, W, Cout, generator=g), backend)
+    cinp, coutp, cpad = layout.planes(Cin), layout.planes(Cout), 16
+    xd, Gd = p4(x.numpy()), p4(G.numpy())
+    ws_bytes = lib.dincae_conv3x3_wgrad_workspace(cinp, 0, cpad, B, H, W)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
+    dw1 = torch.zeros(9, cinp, cpad, 4, device="cuda")
+    db1 = torch.zeros(cpad, device="cuda")
+    check(lib.dincae_conv3x3_wgrad(ptr(xd), cinp, 0, None, 0, ptr(Gd), None, None, SLOPE, coutp, cpad,
+                                   B, H, W, ptr(dw1), ptr(db1), ptr(ws), ws_bytes, stream()))
+    dw2, db2 = torch.zeros_like(dw1), torch.zeros_like(db1)
+    n = ctypes.c_int(0)
+    check(lib.dincae_conv3x3_wgrad_partial(ptr(xd), cinp, 0, None, 0, ptr(Gd), None, None, SLOPE, coutp,
+                                           cpad, B, H, W, ptr(ws), ws_bytes, ctypes.byref(n), stream()))
+    assert n.value >= 1
+    check(lib.dincae_conv3x3_wgrad_reduce(ptr(ws), n.value, cinp, coutp, cpad, ptr(dw2), ptr(db2), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(dw1, dw2) and torch.equal(db1, db2)
+    assert lib.dincae_conv3x3_wgrad_reduce(None, 1, cinp, coutp, cpad, ptr(dw2), ptr(db2), stream()) == -1
+
+
 def test_invalid_arguments_are_rejected():
     lib = _lib.load()
     x = torch.zeros(16, device="cuda")
