@@ -159,8 +159,19 @@ __device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, 
   }
 }
 
+#ifdef DINCAE_TC_TIMELINE
+__device__ long long wg_dbg[3 * 2048];
+#define WG_MARK(code) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { const int r_ = (code) / 100 - 1; \
+  if (wg_k[r_] < 1023) { wg_dbg[r_ * 2048 + 2 * wg_k[r_]] = clock64(); wg_dbg[r_ * 2048 + 2 * wg_k[r_] + 1] = (code); ++wg_k[r_]; } } } while (0)
+#else
+#define WG_MARK(code)
+#endif
+
 template <int GMODE>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const WgTcParams P) {
+#ifdef DINCAE_TC_TIMELINE
+  int wg_k[3] = {0, 0, 0};
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t full_bar[WG_STAGES];
@@ -227,12 +238,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
       // ---- pass A ---------------------------------------------------------------------------
       nxt = wg_next(cur, n_pad, gridDim.x);
       if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
+      if (warp == 0) WG_MARK(100);
       if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (warp == 0) WG_MARK(101);
       wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, va, sa);
+      if (warp == 0) WG_MARK(102);
       if (nxt.tile != cur.tile) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (warp == 0) WG_MARK(103);
         if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
       }
       cur = nxt;
@@ -240,12 +255,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
       // ---- pass B (buffers swapped) ------------------------------------------------------------
       nxt = wg_next(cur, n_pad, gridDim.x);
       if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
+      if (warp == 0) WG_MARK(100);
       if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (warp == 0) WG_MARK(101);
       wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, vb, sbb);
+      if (warp == 0) WG_MARK(102);
       if (nxt.tile != cur.tile) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (warp == 0) WG_MARK(103);
         if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
       }
       cur = nxt;
@@ -261,8 +280,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
     uint32_t ph = 0;
     uint32_t first = 0;                         // 0 until the accumulators hold a value
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      WG_MARK(200);
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
+      WG_MARK(201);
       if (elect_one()) {
         const uint32_t u_lo = smem_u32(ring + s * P.stage_floats) >> 4;
         const uint32_t g_lo = u_lo + (uint32_t)(P.u_floats >> 2);
@@ -285,6 +306,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
+      WG_MARK(202);
       if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
     }
     if (elect_one()) umma_commit(&done_bar);
@@ -427,3 +449,14 @@ int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, 
 }
 
 }  // namespace dincae
+
+#ifdef DINCAE_TC_TIMELINE
+extern "C" int dincae_debug_timeline_wg(long long* host_out, int reset) {
+  if (host_out) cudaMemcpyFromSymbol(host_out, dincae::wg_dbg, sizeof(long long) * 3 * 2048);
+  if (reset) {
+    static long long zeros[3 * 2048];
+    cudaMemcpyToSymbol(dincae::wg_dbg, zeros, sizeof(zeros));
+  }
+  return 3 * 1024;
+}
+#endif

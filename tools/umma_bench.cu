@@ -8,12 +8,6 @@
 
 using namespace dincae;
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-
 struct Cfg {
   int M, N;            // MMA shape
   int a_mn, b_mn;      // 1 = MN-major operand
@@ -100,6 +94,14 @@ int main() {
       {"wgr  M64  N16  A,B mn-major sbo1824", {64, 16, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
       {"wgr  M128 N64  A,B mn-major sbo1824", {128, 64, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
       {"wgr  M64  N64  A,B mn-major sbo1824", {64, 64, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
+      // K-major transposed tiles of the weight gradient: 144-byte core-matrix pitch (bank pad)
+      // vs 128-byte aligned core matrices; shift = one K step (2 pixel groups)
+      {"wgK  M64  N48  K-major sbo144 lbo304/880", {64, 48, 0, 0, 144, 304, 144, 880, 4096, 38, 1}},
+      {"wgK  M64  N48  K-major sbo128 lbo256/768", {64, 48, 0, 0, 128, 256, 128, 768, 4096, 32, 1}},
+      {"wgK  M64  N24  K-major sbo144 lbo592/432", {64, 24, 0, 0, 144, 592, 144, 432, 4096, 74, 1}},
+      {"wgK  M64  N24  K-major sbo128 lbo512/384", {64, 24, 0, 0, 128, 512, 128, 384, 4096, 64, 1}},
+      {"wgK  M128 N120 K-major sbo144 lbo1744", {128, 120, 0, 0, 144, 1744, 144, 2176, 4096, 218, 1}},
+      {"wgK  M128 N120 K-major sbo128 lbo1536", {128, 120, 0, 0, 128, 1536, 128, 1920, 4096, 192, 1}},
   };
   for (auto& nc : cases) {
     for (int grid : {1, 148}) {
