@@ -103,3 +103,41 @@ def test_user_generators_take_the_host_feed_path(tmp_path):
     assert len(loss) == 2 * 3 and np.isfinite(loss).all()
     from dincae_b200 import ncio
     assert ncio.read_recon(fname)["mean_rec"].shape == (T, H, W)
+
+
+def test_config_d_shapes_train_and_reconstruct():
+    """BASELINE.json configs[3] shapes (512x512, 4 variables -> nvar 28, encoder
+    [32,48,72,108,162], 689 M parameters): the layers the tensor-core kernels do not cover
+    (image wider than 128 for the weight gradient, more than 96 output channels) take the
+    FFMA kernels behind the same entry points; a few steps must run, stay finite and learn."""
+    import random
+    import torch
+    from dincae_b200.data import DeviceCube
+    from dincae_b200.engine import Plan
+    from dincae_b200.sampler import TrainSampler
+    from dincae_b200.trainer import Reconstructor, Trainer
+    from tests.util import random_cube
+    rs = np.random.RandomState(5)
+    T, H, W, B = 6, 512, 512, 2
+    lon, lat, time_, fields = random_cube(rs, T, H, W, 4)
+    missing = [np.ma.getmaskarray(f) for f in fields]
+    cube = DeviceCube(lon, lat, time_, fields, missing, [1.0] * 4, 3)
+    assert cube.nvar == 28
+    plan = Plan(H, W, cube.nvar, (32, 48, 72, 108, 162), (0.2,), (1, 2, 3, 4, 5))
+    assert plan.n_params_tf == 688723466            # SURVEY.md section 8d
+    tr = Trainer(plan, cube, B, noise_seed=1, jitter_std=[0.05] * 4, use_graph=False)
+    tr.set_lr(1e-3)
+    random.seed(3)
+    sm = TrainSampler(T, B, 4, seed=7)
+    losses = []
+    for _ in range(3):
+        tr.train_step(*sm.next_batch())
+        losses += tr.flush_losses()
+    assert all(np.isfinite(c) and np.isfinite(r) for c, r in losses)
+    rec = Reconstructor(plan, cube, B, net=tr.net, use_graph=False)
+    out = rec.run_batch(np.arange(B))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all())
+    assert float(out[1].min()) > 0.0                # sigma^2 > 0
+    del tr, rec, cube
+    torch.cuda.empty_cache()
