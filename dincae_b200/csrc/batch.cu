@@ -98,6 +98,11 @@ struct BatchParams {
 
 // One thread per (b, y, x).  All nvar channels of the pixel are produced plane by plane
 // (float4 stores, coalesced along x).
+// ND / WIN > 0: number of variables and time window known at compile time (<1,3> = the
+// default SST configuration): the channel decode folds to constants, the plane loop unrolls and
+// all loads of a pixel (missing / anomaly of the 3 frames, added-cloud mask) are independent
+// and in flight together.  <0,0>: any configuration, run-time decode.
+template <int ND, int WIN>
 __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
   pdl_trigger();
   pdl_wait();
@@ -110,12 +115,15 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
     const int p = (int)(gid - (long long)b * HW);
     const int y = p / P.W, x = p - y * P.W;
     const int i = P.frame_idx[b];
-    const int nd = P.ndata, nd2 = 2 * nd;
+    const int nd = ND ? ND : P.ndata, nd2 = 2 * nd;
+    const int win = WIN ? WIN : P.ntime_win;
+    constexpr int NPL = (2 * ND * WIN + 4 + 3) / 4;
+    const int n_planes = ND ? NPL : P.nvar_planes;
     const size_t THW = (size_t)P.T * HW;
     const bool train = P.cloud_idx != nullptr;
     const int ic = train ? P.cloud_idx[b] : 0;
-    const int nvar = nd2 * P.ntime_win + 4;
-    const int half = P.ntime_win / 2;
+    const int nvar = nd2 * win + 4;
+    const int half = win / 2;
 
     // jitter slots per variable j: channels 2j, 2j+2nd+4, 2j+4nd+4 (reference quirk Q4)
     uint4 rnd = make_uint4(0, 0, 0, 0);
@@ -123,7 +131,8 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
     int gauss_j = -1;
 
     float lane[4];
-    for (int plane = 0; plane < P.nvar_planes; ++plane) {
+#pragma unroll(ND ? NPL : 1)
+    for (int plane = 0; plane < n_planes; ++plane) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = plane * 4 + k;
@@ -253,6 +262,9 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   const long long total = (long long)B * H * W;
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  launch_k(build_batch_kernel, blocks, threads, 0, (cudaStream_t)stream, P);
+  if (ndata == 1 && ntime_win == 3 && nvar_planes == 3)
+    launch_k(build_batch_kernel<1, 3>, blocks, threads, 0, (cudaStream_t)stream, P);
+  else
+    launch_k(build_batch_kernel<0, 0>, blocks, threads, 0, (cudaStream_t)stream, P);
   return check_launch();
 }
