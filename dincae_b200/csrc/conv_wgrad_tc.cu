@@ -65,11 +65,12 @@ struct WgPass {
   int tile, it;
 };
 
-__device__ __forceinline__ WgPass wg_next(WgPass c, int n_pad, int grid) {
-  c.it += WG_LOAD_WARPS;
+// next pass of a warp that takes items first, first + step, ... of every `tile_stride`-th tile
+__device__ __forceinline__ WgPass wg_next(WgPass c, int n_pad, int first, int step, int tile_stride) {
+  c.it += step;
   if (c.it >= n_pad) {
-    c.it -= (c.it / WG_LOAD_WARPS) * WG_LOAD_WARPS;      // back to this warp's first item
-    c.tile += grid;
+    c.it = first;
+    c.tile += tile_stride;
   }
   return c;
 }
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
   }
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
-      mbar_init(&full_bar[s], WG_LOAD_WARPS);
+      mbar_init(&full_bar[s], WG_LOAD_WARPS / 2);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&done_bar, 1);
@@ -223,49 +224,60 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
   if (warp < WG_LOAD_WARPS) {
     // =============================== transposing loader ======================================
     // Item = 128 consecutive pixels (tile-linear index p = row * TW + x) of one plane.  The
-    // warp's items of all its tiles form one stream of passes that is software-pipelined: the
-    // loads of pass n+1 (4 float4 per lane) are in flight while pass n is converted and
-    // stored, across stage and tile boundaries, so the memory latency is paid once.
-    const int n_pad = P.n_items > WG_LOAD_WARPS ? P.n_items : WG_LOAD_WARPS;   // every warp arrives per tile
+    // loader warps form two groups: group g stages the CTA's tiles g, g+2, ... into stage g,
+    // so that while one group waits for its loads the other converts and stores.  Inside a
+    // tile a warp's passes are software-pipelined (loads of pass n+1 in flight while pass n
+    // is stored); the loads of the group's NEXT tile are only issued after the stage has
+    // been published, because the proxy fence in front of the mbarrier arrive (MEMBAR) would
+    // otherwise wait for them.
+    constexpr int GW = WG_LOAD_WARPS / 2;                    // warps per group
+    const int grp = warp / GW, wl = warp - grp * GW;
+    const int n_pad = P.n_items > GW ? P.n_items : GW;       // every warp arrives per tile
+    const int tstride = 2 * gridDim.x;
+    float* stage = ring + grp * P.stage_floats;
     WgPass cur, nxt;
-    cur.tile = blockIdx.x; cur.it = warp;
+    cur.tile = blockIdx.x + grp * gridDim.x;
+    cur.it = wl;
     float4 va[4], vb[4];
     unsigned sa[4], sbb[4];
-    int s = 0;
     uint32_t ph = 0;
     if (cur.tile < P.n_tiles) wg_issue<GMODE>(P, cur, lane, item_tab, va, sa);
     while (cur.tile < P.n_tiles) {
       // ---- pass A ---------------------------------------------------------------------------
-      nxt = wg_next(cur, n_pad, gridDim.x);
-      if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
+      nxt = wg_next(cur, n_pad, wl, GW, tstride);
+      bool last = nxt.tile != cur.tile;
+      if (!last) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
       if (warp == 0) WG_MARK(100);
-      if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (cur.it == wl) mbar_wait(&empty_bar[grp], ph ^ 1u);
       if (warp == 0) WG_MARK(101);
-      wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, va, sa);
+      wg_commit<GMODE>(P, cur, lane, item_tab, stage, va, sa);
       if (warp == 0) WG_MARK(102);
-      if (nxt.tile != cur.tile) {
+      if (last) {
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (lane == 0) mbar_arrive(&full_bar[grp]);
         if (warp == 0) WG_MARK(103);
-        if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+        ph ^= 1u;
+        if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
       }
       cur = nxt;
       if (cur.tile >= P.n_tiles) break;
       // ---- pass B (buffers swapped) ------------------------------------------------------------
-      nxt = wg_next(cur, n_pad, gridDim.x);
-      if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
+      nxt = wg_next(cur, n_pad, wl, GW, tstride);
+      last = nxt.tile != cur.tile;
+      if (!last) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
       if (warp == 0) WG_MARK(100);
-      if (cur.it == warp) mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (cur.it == wl) mbar_wait(&empty_bar[grp], ph ^ 1u);
       if (warp == 0) WG_MARK(101);
-      wg_commit<GMODE>(P, cur, lane, item_tab, ring + s * P.stage_floats, vb, sbb);
+      wg_commit<GMODE>(P, cur, lane, item_tab, stage, vb, sbb);
       if (warp == 0) WG_MARK(102);
-      if (nxt.tile != cur.tile) {
+      if (last) {
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (lane == 0) mbar_arrive(&full_bar[grp]);
         if (warp == 0) WG_MARK(103);
-        if (++s == WG_STAGES) { s = 0; ph ^= 1u; }
+        ph ^= 1u;
+        if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
       }
       cur = nxt;
     }
