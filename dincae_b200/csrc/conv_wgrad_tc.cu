@@ -325,20 +325,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
     __syncwarp();
   }
 
-  // =============================== epilogue (loader warps 0-3) ================================
-  if (warp < 4) {
+  // =============================== epilogue (all loader warps) ================================
+  // TMEM lane quadrant = warp % 4; the warps of a quadrant share its 8-column chunks.
+  if (warp < WG_LOAD_WARPS) {
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    const int q = warp;
+    const int q = warp & 3, part = warp >> 2;
+    constexpr int PARTS = WG_LOAD_WARPS / 4;
     const int m = P.M == 64 ? (lane < 16 ? 16 * q + lane : -1) : 32 * q + lane;
     float* out = P.partial + (size_t)blockIdx.x * (P.wsize + P.cout_pad);
     const int cout8 = P.cgg * 8;
     const bool row_w = m >= 0 && m < 4 * P.kp;
     const bool row_b = m == P.ones_row;
+    int chunk = 0;
     for (int dy = 0; dy < 3; ++dy) {
       for (int dx = 0; dx < 3; ++dx) {
         const int tap = dy * 3 + dx;
-        for (int c0 = 0; c0 < cout8; c0 += 8) {
+        for (int c0 = 0; c0 < cout8; c0 += 8, ++chunk) {
+          if (chunk % PARTS != part) continue;                       // warp-uniform
           float a[8];
           tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dy * P.N + dx * cout8 + c0), a);
 #pragma unroll
