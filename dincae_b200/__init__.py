@@ -8,7 +8,7 @@ Importing the package does not need a GPU; calling any compute entry point does,
 fails loudly if the CUDA extension (libdincae_b200.so) is missing -- there is no CPU path.
 """
 from .api import (FrameSource, NEAREST_NEIGHBOR, data_generator, data_generator_list, identity,
-                  load_gridded_nc, reconstruct, reconstruct_gridded_files,
+                  load_checkpoint, load_gridded_nc, reconstruct, reconstruct_gridded_files,
                   reconstruct_gridded_nc, save_checkpoint, savesample, sinv)
 from .ensemble import EnsembleAccumulator, average_reconstructions
 

@@ -359,6 +359,27 @@ def save_checkpoint(path, trainer):
     return path + ".pt"
 
 
+def load_checkpoint(path, trainer):
+    """Restore what ``save_checkpoint`` wrote (variables, Adam slots and running beta powers,
+    step counter) into a trainer built for the same architecture -- the resume path the
+    reference lacks.  ``path`` with or without the ``.pt`` suffix."""
+    import numpy as np
+    import torch
+    if not path.endswith(".pt"):
+        path = path + ".pt"
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    net = trainer.net
+    names = [e["name"] for e in net.plan.entries]
+    if list(ck["names"]) != names:
+        raise ValueError("checkpoint variables %s do not match the network %s" % (ck["names"][:3], names[:3]))
+    net.set_params_tf(ck["params"])
+    net.adam_m.copy_(torch.from_numpy(net.plan.pack(ck["adam_m"])))
+    net.adam_v.copy_(torch.from_numpy(net.plan.pack(ck["adam_v"])))
+    net.adam_state.copy_(torch.from_numpy(np.asarray(ck["adam_state"], dtype=np.float32)))
+    trainer.step_count = int(ck["step"])
+    return trainer
+
+
 def reconstruct_gridded_nc(filename, varname, outdir, jitter_std=0.05, ntime_win=3,
                            transfun=(identity, identity), **kwargs):
     """(:704-740).  Bug-compatible with the reference: ``transfun[0]`` is not applied to the
