@@ -66,7 +66,9 @@ class DeviceCube:
                 raise ValueError("shape are not coherent")     # :171-172
             nomask = field.mask is np.ma.nomask
             miss = np.ma.getmaskarray(field)
-            if missing is not None and not np.array_equal(np.asarray(missing[i], dtype=bool), miss):
+            # (identity first: comparing two T*H*W masks on the host costs tens of milliseconds)
+            if missing is not None and missing[i] is not miss and \
+                    not np.array_equal(np.asarray(missing[i], dtype=bool), miss):
                 # the reference lays `missing` (not data.mask) over the frame as added clouds
                 if self.cloud_missing is None:
                     self.cloud_missing = torch.empty_like(self.missing)
