@@ -66,10 +66,13 @@ def make_cube(a, pinned):
     from dincae_b200 import synthetic
     lon, lat, time_, data, mask = synthetic.sst_like_cube(T=a.ntime, H=a.size, W=a.size, seed=12345)
     if pinned:
+        # both halves of the masked array (values and mask) live in pinned host memory
         raw = torch.empty(data.shape, dtype=torch.float32).pin_memory()
         raw.copy_(torch.from_numpy(np.ma.getdata(data)))
-        data = np.ma.masked_array(raw.numpy(), np.ma.getmaskarray(data))
-        data._pinned_owner = raw
+        mk = torch.empty(data.shape, dtype=torch.bool).pin_memory()
+        mk.copy_(torch.from_numpy(np.ma.getmaskarray(data)))
+        data = np.ma.masked_array(raw.numpy(), mk.numpy())
+        data._pinned_owner = (raw, mk)
     return lon, lat, time_, data, mask
 
 

@@ -5,25 +5,47 @@
 namespace dincae {
 
 // ---------------------------------------------------------------------------------------
-// prepare_cube: one thread per pixel walks the time axis twice (coalesced across pixels).
-// numpy's MaskedArray.mean over axis 0 adds the 0-filled float32 slices in time order,
-// then divides in float64; the anomaly and the division by obs_var are float64 too and are
-// rounded to float32 once when stored (DINCAE/__init__.py:168-169,180).
+// prepare_cube: numpy's MaskedArray.mean over axis 0 adds the 0-filled float32 slices in
+// time order, then divides in float64; the anomaly and the division by obs_var are float64
+// too and are rounded to float32 once when stored (DINCAE/__init__.py:168-169,180).
+// Two kernels.  (1) cube_mean_kernel: the float32 sum of a pixel must run in time order, so a
+// thread owns a pixel (coalesced across pixels) -- with only H*W threads the pass is bound by
+// load latency, hence PC_UNROLL time steps are fetched into registers (all loads independent,
+// in flight together) before the ordered adds.  (2) cube_anom_kernel: one thread per 4
+// consecutive elements of the T*H*W cube, fully parallel.
 // ---------------------------------------------------------------------------------------
-__global__ void prepare_cube_kernel(const float* __restrict__ data,
-                                    const uint8_t* __restrict__ missing, int T, size_t HW,
-                                    double obs_var, int nomask, float* __restrict__ anom,
-                                    double* __restrict__ meandata, uint8_t* __restrict__ never) {
+constexpr int PC_UNROLL = 32;
+
+__global__ void __launch_bounds__(64) cube_mean_kernel(const float* __restrict__ data,
+                                                       const uint8_t* __restrict__ missing, int T, size_t HW,
+                                                       int nomask, double* __restrict__ meandata,
+                                                       uint8_t* __restrict__ never) {
   pdl_trigger();
   pdl_wait();
-  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
+  const float* d = data + p;
+  const uint8_t* m = missing + p;
   float sum = 0.f;
   int count = 0;
-  for (int t = 0; t < T; ++t) {
-    const bool miss = missing[(size_t)t * HW + p] != 0;
-    const float v = miss ? 0.f : data[(size_t)t * HW + p];
-    sum = __fadd_rn(sum, v);
+  int t = 0;
+  for (; t + PC_UNROLL <= T; t += PC_UNROLL) {
+    float v[PC_UNROLL];
+    uint8_t k[PC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PC_UNROLL; ++u) {
+      v[u] = __ldg(d + (size_t)(t + u) * HW);
+      k[u] = __ldg(m + (size_t)(t + u) * HW);
+    }
+#pragma unroll
+    for (int u = 0; u < PC_UNROLL; ++u) {
+      sum = __fadd_rn(sum, k[u] ? 0.f : v[u]);
+      count += k[u] ? 0 : 1;
+    }
+  }
+  for (; t < T; ++t) {
+    const bool miss = m[(size_t)t * HW] != 0;
+    sum = __fadd_rn(sum, miss ? 0.f : d[(size_t)t * HW]);
     count += miss ? 0 : 1;
   }
   double mean;
@@ -34,14 +56,42 @@ __global__ void prepare_cube_kernel(const float* __restrict__ data,
   }
   meandata[p] = mean;
   never[p] = (count == 0) ? 1 : 0;
-  for (int t = 0; t < T; ++t) {
-    const bool miss = missing[(size_t)t * HW + p] != 0;
-    float a = 0.f;
-    if (!miss && count > 0) {
-      const double d = __dsub_rn((double)data[(size_t)t * HW + p], mean);
-      a = (float)__ddiv_rn(d, obs_var);
-    }
-    anom[(size_t)t * HW + p] = a;
+}
+
+__device__ __forceinline__ float cube_anom1(float v, bool miss, double mean, bool nev, double obs_var) {
+  if (miss || nev) return 0.f;
+  return (float)__ddiv_rn(__dsub_rn((double)v, mean), obs_var);
+}
+
+// VEC = 4: H*W is a multiple of 4 and the buffers are 16-byte aligned (a quad never crosses a frame)
+template <int VEC>
+__global__ void __launch_bounds__(256) cube_anom_kernel(const float* __restrict__ data,
+                                                        const uint8_t* __restrict__ missing, size_t n_items,
+                                                        size_t HW, double obs_var,
+                                                        const double* __restrict__ meandata,
+                                                        const uint8_t* __restrict__ never,
+                                                        float* __restrict__ anom) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  if (VEC == 4) {
+    const size_t e = 4 * i;
+    const size_t p = e % HW;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(data) + i);
+    const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(missing) + i);
+    const double2 m01 = __ldg(reinterpret_cast<const double2*>(meandata + p));
+    const double2 m23 = __ldg(reinterpret_cast<const double2*>(meandata + p) + 1);
+    const uchar4 nv = __ldg(reinterpret_cast<const uchar4*>(never + p));
+    float4 o;
+    o.x = cube_anom1(v.x, k.x != 0, m01.x, nv.x != 0, obs_var);
+    o.y = cube_anom1(v.y, k.y != 0, m01.y, nv.y != 0, obs_var);
+    o.z = cube_anom1(v.z, k.z != 0, m23.x, nv.z != 0, obs_var);
+    o.w = cube_anom1(v.w, k.w != 0, m23.y, nv.w != 0, obs_var);
+    reinterpret_cast<float4*>(anom)[i] = o;
+  } else {
+    const size_t p = i % HW;
+    anom[i] = cube_anom1(data[i], missing[i] != 0, meandata[p], never[p] != 0, obs_var);
   }
 }
 
@@ -221,10 +271,19 @@ extern "C" int dincae_prepare_cube(const float* data, const uint8_t* missing, in
   if (!data || !missing || !anom || !meandata || !never || T <= 0 || H <= 0 || W <= 0)
     return DINCAE_EINVAL;
   const size_t HW = (size_t)H * W;
-  const int threads = 128;
-  const unsigned blocks = (unsigned)((HW + threads - 1) / threads);
-  launch_k(prepare_cube_kernel, blocks, threads, 0, (cudaStream_t)stream, 
-      data, missing, T, HW, obs_var, nomask, anom, meandata, never);
+  const cudaStream_t st = (cudaStream_t)stream;
+  launch_k(cube_mean_kernel, (unsigned)((HW + 63) / 64), 64, 0, st, data, missing, T, HW, nomask, meandata, never);
+  const size_t n = HW * (size_t)T;
+  const bool vec = (HW % 4 == 0) && (((uintptr_t)data | (uintptr_t)missing | (uintptr_t)anom |
+                                      (uintptr_t)never) % 16 == 0) && ((uintptr_t)meandata % 16 == 0);
+  const size_t items = vec ? n / 4 : n;
+  if ((items + 255) / 256 > 0x7fffffffull) return DINCAE_EINVAL;
+  if (vec)
+    launch_k(cube_anom_kernel<4>, (unsigned)((items + 255) / 256), 256, 0, st, data, missing, items, HW, obs_var,
+             (const double*)meandata, (const uint8_t*)never, anom);
+  else
+    launch_k(cube_anom_kernel<1>, (unsigned)((items + 255) / 256), 256, 0, st, data, missing, items, HW, obs_var,
+             (const double*)meandata, (const uint8_t*)never, anom);
   return check_launch();
 }
 

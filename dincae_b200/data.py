@@ -17,6 +17,17 @@ def day_of_year(time):
     return np.array([t.timetuple().tm_yday for t in time])
 
 
+def _same_buffer(a, b):
+    """True when two arrays are the same view of the same memory (np.ma hands out a fresh view
+    object of a field's mask on every access, so ``is`` does not see it)."""
+    if a is b:
+        return True
+    if not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray)):
+        return False
+    return (a.dtype == b.dtype and a.shape == b.shape and a.strides == b.strides and
+            a.__array_interface__["data"][0] == b.__array_interface__["data"][0])
+
+
 class DeviceCube:
     def __init__(self, lon, lat, time, data_full, missing, obs_err_std=None, ntime_win=3,
                  device=None):
@@ -66,8 +77,8 @@ class DeviceCube:
                 raise ValueError("shape are not coherent")     # :171-172
             nomask = field.mask is np.ma.nomask
             miss = np.ma.getmaskarray(field)
-            # (identity first: comparing two T*H*W masks on the host costs tens of milliseconds)
-            if missing is not None and missing[i] is not miss and \
+            # (same memory first: comparing two T*H*W masks on the host costs tens of milliseconds)
+            if missing is not None and not _same_buffer(missing[i], miss) and \
                     not np.array_equal(np.asarray(missing[i], dtype=bool), miss):
                 # the reference lays `missing` (not data.mask) over the frame as added clouds
                 if self.cloud_missing is None:

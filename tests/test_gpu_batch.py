@@ -121,6 +121,29 @@ def test_unmasked_input_takes_float32_mean_path():
     assert np.array_equal(xin, want)
 
 
+@pytest.mark.parametrize("T,H,W,nf", [(70, 8, 12, 2), (70, 5, 7, 1), (33, 4, 4, 1)])
+def test_prepare_cube_long_time_axis(T, H, W, nf):
+    """Time axes longer than the mean kernel's register window (ordered float32 sum across
+    several windows + a tail) through both anomaly kernels (vectorised: H*W % 4 == 0)."""
+    from dincae_b200.data import DeviceCube
+    rs = np.random.RandomState(T + H)
+    lon, lat, time, fields = random_cube(rs, T, H, W, nf)
+    fields[0][:, 1, 1] = np.ma.masked                      # a second never-observed pixel
+    missing = [np.ma.getmaskarray(f) for f in fields]
+    oes = list(rs.uniform(0.5, 2.0, nf))
+    feat = datagen_np.StaticFeatures(lon, lat, time, fields, oes)
+    cube = DeviceCube(lon, lat, time, fields, missing, oes, 3)
+    for k in range(nf):
+        want = fields[k].mean(axis=0, keepdims=True)
+        assert np.array_equal(np.ma.getmaskarray(cube.meandata[k]), np.ma.getmaskarray(want))
+        keep = ~np.ma.getmaskarray(want)
+        assert np.array_equal(np.ma.getdata(cube.meandata[k])[keep], np.ma.getdata(want)[keep])
+    xin, xtrue, _ = build(cube, np.arange(T), None, None, [0.0] * nf, T)
+    want = np.stack([datagen_np.stack_frame(feat, i, 3) for i in range(T)])
+    assert np.array_equal(xin, want)
+    assert np.array_equal(xtrue, feat.x[:, :, :, 0:2])
+
+
 def test_philox_jitter_statistics_and_determinism():
     """Production noise: N(0, jitter^2) on the three data channels, reproducible, keyed by
     the frame's sequence number (not by its slot in the batch)."""

@@ -230,3 +230,18 @@ def test_ensemble_oracle_definitions():
     assert np.allclose(np.ma.getdata(sg)[:2], [1.0, 2.0])
     mu, sg = ensemble_np.average([m1, m2], [s1, s2], "mixture")
     assert np.allclose(np.ma.getdata(sg)[:2], [np.sqrt(1.0 + 1.0), 2.0])
+
+
+def test_same_buffer_sees_through_fresh_mask_views():
+    """np.ma returns a new view object of a field's mask on every access; DeviceCube.upload must
+    recognise it as the caller's `missing` without comparing T*H*W booleans on the host."""
+    from dincae_b200.data import _same_buffer
+    d = np.zeros((5, 4, 3), "f4")
+    m = np.zeros((5, 4, 3), bool)
+    data = np.ma.masked_array(d, m)
+    assert np.ma.getmaskarray(np.ma.asarray(data)) is not np.ma.getmaskarray(data)
+    assert _same_buffer(np.ma.getmaskarray(np.ma.asarray(data)), np.ma.getmaskarray(data))
+    assert not _same_buffer(m.copy(), m)
+    assert not _same_buffer(m[1:], m[:-1])
+    assert not _same_buffer(m.view(np.uint8), m)
+    assert not _same_buffer([True], m)
