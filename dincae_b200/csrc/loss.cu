@@ -30,6 +30,36 @@ __global__ void __launch_bounds__(256) head_recon_kernel(const float4* __restric
   s2_rec[i] = s2;
 }
 
+// Head + what `savesample` does per batch (DINCAE/__init__.py:237-248, 288-291), written as
+// the records of the output file: record b = [mean_rec[b] | sigma_rec[b]], each H*W float32,
+// mean_rec = float32(float64(m_rec) + meandata), sigma_rec = sqrt(sigma2_rec), both replaced
+// by the fill value where the pixel was never observed (meandata.mask).  With big_endian the
+// 4 bytes of every value are reversed, so that the buffer is the byte image of NetCDF-3
+// records and the host only has to write it out.
+__global__ void __launch_bounds__(256) head_recon_records_kernel(
+    const float4* __restrict__ xrec, int B, int HW, const double* __restrict__ meandata,
+    const uint8_t* __restrict__ never, float fill, int big_endian, uint32_t* __restrict__ records) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  const int b = (int)(i / HW), p = (int)(i - (size_t)b * HW);
+  const float4 r = __ldg(&xrec[i]);
+  float m, s2, q, dq;
+  head_eval(r.x, r.y, m, s2, q, dq);
+  float mean = (float)__dadd_rn((double)m, __ldg(&meandata[p]));
+  float sigma = __fsqrt_rn(s2);
+  if (never && __ldg(&never[p])) mean = sigma = fill;
+  uint32_t um = __float_as_uint(mean), us = __float_as_uint(sigma);
+  if (big_endian) {
+    um = __byte_perm(um, 0u, 0x0123);
+    us = __byte_perm(us, 0u, 0x0123);
+  }
+  uint32_t* o = records + (size_t)b * 2 * HW + p;
+  o[0] = um;
+  o[HW] = us;
+}
+
 struct LossWork {
   unsigned int counter;
   unsigned int pad[3];
@@ -137,6 +167,18 @@ extern "C" int dincae_head_recon(const float* xrec, int B, int H, int W, float* 
   const size_t n = (size_t)B * H * W;
   launch_k(head_recon_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, 
       reinterpret_cast<const float4*>(xrec), n, m_rec, sigma2_rec);
+  return check_launch();
+}
+
+extern "C" int dincae_head_recon_records(const float* xrec, int B, int H, int W, const double* meandata,
+                                         const uint8_t* never, float fill_value, int big_endian,
+                                         void* records, void* stream) {
+  if (!xrec || !meandata || !records || B <= 0 || H <= 0 || W <= 0) return DINCAE_EINVAL;
+  if ((long long)H * W >= (1ll << 30)) return DINCAE_EINVAL;
+  const size_t n = (size_t)B * H * W;
+  launch_k(head_recon_records_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+           reinterpret_cast<const float4*>(xrec), B, H * W, meandata, never, fill_value, big_endian,
+           reinterpret_cast<uint32_t*>(records));
   return check_launch();
 }
 
