@@ -397,6 +397,20 @@ def run_ours(a):
         torch.cuda.synchronize()
         line["recon_fps"] = nrec_frames / (time.perf_counter() - t0)
 
+        # ---- the same sweep through to the output file (a12: forward + savesample arithmetic on
+        #      the device, records written by threads; NetCDF-3 unless netCDF4 is installed) -----
+        import tempfile
+        from dincae_b200 import api
+        rec2 = Reconstructor(plan, cube, B, net=trainer.net, use_graph=not a.no_graph,
+                             records=(cube.meandata[0], -9999.), n_out_slots=api._SAVE_SLOTS)
+        with tempfile.TemporaryDirectory() as d:
+            api._save_records(rec2, os.path.join(d, "warm.nc"), lon, lat, cube.meandata[0], 2 * B + (a.ntime % B), B)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            api._save_records(rec2, os.path.join(d, "data.nc"), lon, lat, cube.meandata[0], a.ntime, B)
+            line["recon_to_file_fps"] = a.ntime / (time.perf_counter() - t0)
+            line["recon_file_bytes"] = os.path.getsize(os.path.join(d, "data.nc"))
+
         if not a.no_cpu_baseline:
             cb = cpu_arm(a, a.cpu_steps, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

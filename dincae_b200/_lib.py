@@ -43,7 +43,7 @@ SIGNATURES = {
     "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_weight": (c_int, [vp, vp, c_int, c_int, c_int, vp, vp, vp]),
     "dincae_head_recon": (c_int, [vp, c_int, c_int, c_int, vp, vp, vp]),
-    "dincae_head_recon_records": (c_int, [vp, c_int, c_int, c_int, vp, vp, c_float, c_int, vp, vp]),
+    "dincae_head_recon_records": (c_int, [vp, c_int, c_int, c_int, vp, vp, c_float, c_int, c_int, vp, vp]),
     "dincae_head_loss_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_head_loss": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_float, vp, vp, vp, vp, vp,
                                  c_size_t, vp]),

@@ -147,7 +147,9 @@ def data_generator(lon, lat, time, data_full, missing, train=True, ntime_win=3, 
 def savesample(fname, m_rec, σ2_rec, meandata, lon, lat, e, ii, offset,
                transfun=(identity, identity)):
     """(:234-294) write one batch of the reconstruction; creates the file at ``ii == 0``."""
-    recdata = transfun[1](m_rec + meandata)
+    # (masked entries of meandata are masked again by the writer: plain arithmetic here)
+    md = np.ma.asarray(meandata)
+    recdata = transfun[1](m_rec + (np.ma.getdata(md) if md.mask is np.ma.nomask else md.filled(0)))
     if transfun[1] not in (np.exp, identity):
         print("warning: sigma_rec is not transformed")
     sigma_rec = np.sqrt(σ2_rec)
@@ -269,9 +271,16 @@ def reconstruct(lon, lat, mask, meandata,
                       jitter_std=train_datagen.jitter_std)
     sampler = TrainSampler(train_len, batch_size, shuffle_buffer_size, seed=shuffle_seed,
                            train=train_datagen.train)
+    # With the stock `savesample` and no output transform the per-batch arithmetic of
+    # savesample (:237-248, 288-291) runs on the device and the sweep hands file-ready records
+    # to writer threads; any other hook / transform gets (m_rec, sigma2_rec) on the host like
+    # in the reference.
+    fast_save = savesample is globals()["savesample"] and transfun[1] is identity
     recon = Reconstructor(plan, test_cube, batch_size, net=trainer.net,
                           train_mode_inputs=test_datagen.train, noise_seed=noise_seed + 1,
-                          jitter_std=test_datagen.jitter_std)
+                          jitter_std=test_datagen.jitter_std,
+                          records=(meandata, -9999.) if fast_save else None,
+                          n_out_slots=_SAVE_SLOTS if fast_save else 2)
     writer_tb = None
     if tensorboard and outdir is not None:
         try:
@@ -312,17 +321,20 @@ def reconstruct(lon, lat, mask, meandata,
         if ((e == epochs - 1) or ((save_each > 0) and (e % save_each == 0))) and outdir is not None:
             print("Save output", e)
             fname = _output_name(outdir)
-            pending = None
-            for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
-                out = recon.run_batch(frames, slot=ii % 2)
+            if fast_save:
+                _save_records(recon, fname, lon, lat, meandata, test_len, batch_size)
+            else:
+                pending = None
+                for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
+                    out = recon.run_batch(frames, slot=ii % 2)
+                    if pending is not None:
+                        _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    pending = (out, len(frames), ii, ii * batch_size, ev)
                 if pending is not None:
                     _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
-                ev = torch.cuda.Event()
-                ev.record()
-                pending = (out, len(frames), ii, ii * batch_size, ev)
-            if pending is not None:
-                _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
-            _close_writer(fname)
+                _close_writer(fname)
 
         if (save_model_each > 0) and (e % save_model_each == 0) and outdir is not None:
             save_checkpoint(os.path.join(outdir, "model-{:03d}.ckpt".format(e + 1)), trainer)
@@ -333,6 +345,42 @@ def reconstruct(lon, lat, mask, meandata,
     print(dt_end)
     print(dt_end - dt_start)
     return fname
+
+
+_SAVE_SLOTS, _SAVE_THREADS = 6, 3
+
+
+def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size):
+    """Reconstruction sweep of the stock output path (:671-689): the device emits the file's
+    records batch by batch into a ring of pinned buffers; writer threads wait for a batch's
+    copy event and put it into the file with one positional write.  The file is complete and
+    closed on return."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from .sampler import sequential_batches
+    writer = ncio.ReconWriter(fname, lon, lat, meandata)
+    nslots = len(recon.out_host)
+
+    def put(ev, buf, offset, n):
+        ev.synchronize()
+        writer.write_records(offset, buf.numpy().reshape(-1).view(np.uint8), n)
+
+    futures = [None] * nslots
+    try:
+        with ThreadPoolExecutor(max_workers=_SAVE_THREADS) as pool:
+            for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
+                slot = ii % nslots
+                if futures[slot] is not None:
+                    futures[slot].result()             # the slot's previous batch is in the file
+                out = recon.run_batch(frames, slot=slot)
+                ev = torch.cuda.Event()
+                ev.record()
+                futures[slot] = pool.submit(put, ev, out, ii * batch_size, len(frames))
+            for f in futures:
+                if f is not None:
+                    f.result()
+    finally:
+        writer.close()
 
 
 def _emit(savesample_fn, fname, pending, meandata, lon, lat, e, transfun):

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) head_recon_kernel(const float4* __restric
 // records and the host only has to write it out.
 __global__ void __launch_bounds__(256) head_recon_records_kernel(
     const float4* __restrict__ xrec, int B, int HW, const double* __restrict__ meandata,
-    const uint8_t* __restrict__ never, float fill, int big_endian, uint32_t* __restrict__ records) {
+    const uint8_t* __restrict__ never, float fill, int mean_f32, int big_endian,
+    uint32_t* __restrict__ records) {
   pdl_trigger();
   pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +48,10 @@ __global__ void __launch_bounds__(256) head_recon_records_kernel(
   const float4 r = __ldg(&xrec[i]);
   float m, s2, q, dq;
   head_eval(r.x, r.y, m, s2, q, dq);
-  float mean = (float)__dadd_rn((double)m, __ldg(&meandata[p]));
+  // numpy adds in the operands' common type: float64 for the usual (masked -> float64) mean,
+  // float32 when the input had no mask at all and the mean stayed float32
+  const double md = __ldg(&meandata[p]);
+  float mean = mean_f32 ? __fadd_rn(m, (float)md) : (float)__dadd_rn((double)m, md);
   float sigma = __fsqrt_rn(s2);
   if (never && __ldg(&never[p])) mean = sigma = fill;
   uint32_t um = __float_as_uint(mean), us = __float_as_uint(sigma);
@@ -171,13 +175,13 @@ extern "C" int dincae_head_recon(const float* xrec, int B, int H, int W, float* 
 }
 
 extern "C" int dincae_head_recon_records(const float* xrec, int B, int H, int W, const double* meandata,
-                                         const uint8_t* never, float fill_value, int big_endian,
-                                         void* records, void* stream) {
+                                         const uint8_t* never, float fill_value, int mean_is_f32,
+                                         int big_endian, void* records, void* stream) {
   if (!xrec || !meandata || !records || B <= 0 || H <= 0 || W <= 0) return DINCAE_EINVAL;
   if ((long long)H * W >= (1ll << 30)) return DINCAE_EINVAL;
   const size_t n = (size_t)B * H * W;
   launch_k(head_recon_records_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
-           reinterpret_cast<const float4*>(xrec), B, H * W, meandata, never, fill_value, big_endian,
+           reinterpret_cast<const float4*>(xrec), B, H * W, meandata, never, fill_value, mean_is_f32, big_endian,
            reinterpret_cast<uint32_t*>(records));
   return check_launch();
 }

@@ -70,7 +70,8 @@ class DeviceCube:
         """(Re)load the cube from host arrays into the SAME device buffers (pointers captured
         in CUDA graphs stay valid) and run the temporal-mean pre-pass on the device."""
         nd, T, H, W = self.ndata, self.T, self.H, self.W
-        self.meandata = []
+        if fetch_mean:
+            self.meandata = []
         for i in range(nd):
             field = np.ma.asarray(data_full[i])
             if field.shape != (T, H, W):

@@ -352,6 +352,15 @@ class Network:
             ptr(self.D[P.L]), B, P.H, P.W, ptr(self.m_rec), ptr(self.s2_rec), stream_ptr()),
             16 * B * P.H * P.W, 0)
 
+    def head_recon_records(self, B, meandata, never, fill, mean_is_f32, records, big_endian=True):
+        """Head + the arithmetic of ``savesample`` (:237-248, 288-291) as file-ready records
+        [B][2][H][W] (see include/dincae_b200.h)."""
+        P = self.plan
+        self._call("head_recon_records", "dincae_head_recon_records", (
+            ptr(self.D[P.L]), B, P.H, P.W, ptr(meandata), ptr(never), float(fill), int(mean_is_f32),
+            int(big_endian), ptr(records), stream_ptr()),
+            (16 + 8) * B * P.H * P.W, 0)
+
     # ---- loss + backward --------------------------------------------------------------------
     def grad_buckets(self):
         """(start, end) ranges of the flat gradient buffer in the order they become final

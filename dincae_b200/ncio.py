@@ -9,7 +9,10 @@ xarray / ncdump open both.  ``num2date`` is restated for the CF "<unit> since <d
 strings the reference relies on (:87).
 """
 import datetime
+import os
 import re
+import struct
+import threading
 
 import numpy as np
 
@@ -134,64 +137,178 @@ def write_gridded(fname, varname, lon, lat, time_values, time_units, data, mask,
         dv[:len(time_values)] = filled
 
 
+# ---------------------------------------------------------------------------------------
+# Streaming NetCDF-3 (64-bit offset) writer for the reconstruction file.
+#
+# scipy.io.netcdf_file keeps every variable in memory and re-allocates the record arrays on
+# each append (quadratic in the number of batches: 2.1 s for the 5266 x 112 x 112 cube,
+# 60x the time the GPU needs for the forward sweep).  The classic format is simple enough to
+# emit directly: a fixed header, the fixed-size variables, then one record per time step
+# holding the record variables back to back -- so a batch of n reconstructed frames is ONE
+# contiguous byte range of the file, written with a positional write (no seek state: batches
+# can be written from several threads), and the record count is patched into the header on
+# close.  Format reference: "NetCDF Classic and 64-bit Offset File Formats" (Unidata).
+# ---------------------------------------------------------------------------------------
+_NC_DIMENSION, _NC_VARIABLE, _NC_ATTRIBUTE, _NC_FLOAT = 10, 11, 12, 5
+
+
+def _nc_name(name):
+    raw = name.encode()
+    return struct.pack(">i", len(raw)) + raw + b"\0" * (-len(raw) % 4)
+
+
+def _nc_var(name, dimids, fill, vsize, begin):
+    out = _nc_name(name) + struct.pack(">i", len(dimids)) + b"".join(struct.pack(">i", d) for d in dimids)
+    if fill is None:
+        out += struct.pack(">ii", 0, 0)
+    else:
+        out += struct.pack(">ii", _NC_ATTRIBUTE, 1) + _nc_name("_FillValue") + \
+            struct.pack(">iif", _NC_FLOAT, 1, fill)
+    return out + struct.pack(">iiq", _NC_FLOAT, vsize, begin)
+
+
+class RecordFileWriter:
+    """``outdir/data-*.nc`` with the layout of ``savesample`` (DINCAE/__init__.py:251-278) as a
+    NetCDF-3 64-bit-offset file written in streaming fashion.  Dimensions time (unlimited),
+    lon, lat; float32 variables lon(lon), lat(lat), meandata(lat,lon), mean_rec(time,lat,lon),
+    sigma_rec(time,lat,lon), the last three with ``_FillValue``."""
+
+    def __init__(self, fname, lon, lat, meandata, fill_value=-9999., append=False):
+        self.fname = fname
+        self.nlon, self.nlat = len(lon), len(lat)
+        self.fill = np.float32(fill_value)
+        self.mask = np.ma.getmaskarray(np.ma.asarray(meandata)).reshape(self.nlat, self.nlon)
+        self.vsize = self.nlat * self.nlon * 4
+        self.recsize = 2 * self.vsize
+        header = self._header(0)
+        self.rec_start = len(header) + 4 * self.nlon + 4 * self.nlat + self.vsize
+        self.numrecs = 0
+        self._lock = threading.Lock()
+        if append:
+            # reference: Dataset(fname, 'a') for ii > 0 (:281-283); only files this class wrote
+            with open(fname, "rb") as f:
+                head = f.read(len(header))
+            if len(head) != len(header) or head[:4] != header[:4] or head[8:] != header[8:]:
+                raise ValueError("%s was not written by RecordFileWriter with this grid" % fname)
+            self.numrecs = struct.unpack(">i", head[4:8])[0]
+            self.fd = os.open(fname, os.O_RDWR)
+            return
+        md = np.ma.filled(np.ma.asarray(meandata), fill_value).reshape(self.nlat, self.nlon)
+        self.fd = os.open(fname, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+        fixed = header + np.asarray(lon, dtype=">f4").tobytes() + np.asarray(lat, dtype=">f4").tobytes() + \
+            md.astype(">f4").tobytes()
+        assert len(fixed) == self.rec_start
+        os.pwrite(self.fd, fixed, 0)
+
+    def _header(self, numrecs):
+        nlon, nlat, vs = self.nlon, self.nlat, self.vsize
+        fill = float(self.fill)
+        dims = struct.pack(">ii", _NC_DIMENSION, 3) + _nc_name("time") + struct.pack(">i", 0) + \
+            _nc_name("lon") + struct.pack(">i", nlon) + _nc_name("lat") + struct.pack(">i", nlat)
+        # dimension ids: time 0, lon 1, lat 2.  `begin` offsets depend on the header length,
+        # which does not depend on their values: build once with zeros, then for real.
+        def variables(b_lon, b_lat, b_md, b_rec):
+            return struct.pack(">ii", _NC_VARIABLE, 5) + \
+                _nc_var("lon", [1], None, 4 * nlon, b_lon) + _nc_var("lat", [2], None, 4 * nlat, b_lat) + \
+                _nc_var("meandata", [2, 1], fill, vs, b_md) + \
+                _nc_var("mean_rec", [0, 2, 1], fill, vs, b_rec) + \
+                _nc_var("sigma_rec", [0, 2, 1], fill, vs, b_rec + vs)
+        pre = b"CDF\x02" + struct.pack(">i", numrecs) + dims + struct.pack(">ii", 0, 0)
+        hlen = len(pre) + len(variables(0, 0, 0, 0))
+        b_lon = hlen
+        b_lat = b_lon + 4 * nlon
+        b_md = b_lat + 4 * nlat
+        return pre + variables(b_lon, b_lat, b_md, b_md + vs)
+
+    def write_records(self, offset, records, n=None):
+        """``records``: the byte image of ``n`` records (big-endian float32
+        [n][2][lat][lon], already masked with the fill value), e.g. the pinned host buffer
+        filled by ``dincae_head_recon_records``.  Thread-safe (positional write)."""
+        buf = memoryview(records).cast("B")
+        if n is None:
+            n = len(buf) // self.recsize
+        buf = buf[:n * self.recsize]
+        pos = self.rec_start + offset * self.recsize
+        while len(buf):
+            k = os.pwrite(self.fd, buf, pos)
+            buf = buf[k:]
+            pos += k
+        with self._lock:
+            self.numrecs = max(self.numrecs, offset + n)
+
+    def write(self, offset, mean_rec, sigma_rec):
+        """mean_rec / sigma_rec [n,lat,lon] (host byte order); entries under meandata.mask get
+        the fill value (:288-291)."""
+        n = mean_rec.shape[0]
+        rec = np.empty((n, 2, self.nlat, self.nlon), dtype=">f4")
+        rec[:, 0] = mean_rec
+        rec[:, 1] = sigma_rec
+        rec[:, :, self.mask] = self.fill
+        self.write_records(offset, rec.reshape(-1).view(np.uint8), n)
+
+    def close(self):
+        if self.fd is not None:
+            os.pwrite(self.fd, struct.pack(">i", self.numrecs), 4)
+            os.close(self.fd)
+            self.fd = None
+
+    ds = property(lambda self: self.fd)
+
+
 class ReconWriter:
     """Output file of the reconstruction sweep: same layout as ``savesample``
     (DINCAE/__init__.py:251-278): dims time (unlimited), lon, lat; f4 variables
     lon(lon), lat(lat), meandata(lat,lon), mean_rec(time,lat,lon), sigma_rec(time,lat,lon),
     the last three with _FillValue -9999.  Unlike the reference the file stays open between
-    batches (append = slice assignment on the record dimension)."""
+    batches.  NETCDF4 through netCDF4-python when it is installed (like the reference);
+    otherwise NetCDF-3 through ``RecordFileWriter``."""
 
-    def __init__(self, fname, lon, lat, meandata, fill_value=-9999., append=False):
+    def __new__(cls, fname, lon, lat, meandata, fill_value=-9999., append=False):
+        if _nc4 is None:
+            return RecordFileWriter(fname, lon, lat, meandata, fill_value, append)
+        return super().__new__(cls)
+
+    def __init__(self, fname, lon, lat, meandata, fill_value=-9999., append=False):  # pragma: no cover
         self.fname = fname
         self.fill = np.float32(fill_value)
         self.mask = np.ma.getmaskarray(np.ma.asarray(meandata)).reshape(len(lat), len(lon))
         if append:                      # reference: Dataset(fname, 'a') for ii > 0 (:281-283)
-            self.ds = _nc4.Dataset(fname, "a") if _nc4 is not None else _nc3(fname, "a")
+            self.ds = _nc4.Dataset(fname, "a")
             self.v_mean = self.ds.variables["mean_rec"]
             self.v_sigma = self.ds.variables["sigma_rec"]
             return
         md = np.ma.filled(np.ma.asarray(meandata), fill_value).reshape(len(lat), len(lon))
-        if _nc4 is not None:            # pragma: no cover
-            ds = _nc4.Dataset(fname, "w", format="NETCDF4")
-            ds.createDimension("time", None)
-            ds.createDimension("lon", len(lon))
-            ds.createDimension("lat", len(lat))
-            ds.createVariable("lon", "f4", ("lon",))[:] = lon
-            ds.createVariable("lat", "f4", ("lat",))[:] = lat
-            v = ds.createVariable("meandata", "f4", ("lat", "lon"), fill_value=fill_value)
-            v[:, :] = np.ma.masked_array(md, self.mask)
-            self.v_mean = ds.createVariable("mean_rec", "f4", ("time", "lat", "lon"),
-                                            fill_value=fill_value)
-            self.v_sigma = ds.createVariable("sigma_rec", "f4", ("time", "lat", "lon"),
-                                             fill_value=fill_value)
-            self.ds = ds
-            return
-        ds = _nc3(fname, "w", version=2)
+        ds = _nc4.Dataset(fname, "w", format="NETCDF4")
         ds.createDimension("time", None)
         ds.createDimension("lon", len(lon))
         ds.createDimension("lat", len(lat))
-        ds.createVariable("lon", "f4", ("lon",))[:] = np.asarray(lon, dtype="f4")
-        ds.createVariable("lat", "f4", ("lat",))[:] = np.asarray(lat, dtype="f4")
-        v = ds.createVariable("meandata", "f4", ("lat", "lon"))
-        v._FillValue = self.fill
-        v[:, :] = md.astype("f4")
-        self.v_mean = ds.createVariable("mean_rec", "f4", ("time", "lat", "lon"))
-        self.v_mean._FillValue = self.fill
-        self.v_sigma = ds.createVariable("sigma_rec", "f4", ("time", "lat", "lon"))
-        self.v_sigma._FillValue = self.fill
+        ds.createVariable("lon", "f4", ("lon",))[:] = lon
+        ds.createVariable("lat", "f4", ("lat",))[:] = lat
+        v = ds.createVariable("meandata", "f4", ("lat", "lon"), fill_value=fill_value)
+        v[:, :] = np.ma.masked_array(md, self.mask)
+        self.v_mean = ds.createVariable("mean_rec", "f4", ("time", "lat", "lon"),
+                                        fill_value=fill_value)
+        self.v_sigma = ds.createVariable("sigma_rec", "f4", ("time", "lat", "lon"),
+                                         fill_value=fill_value)
         self.ds = ds
 
-    def write(self, offset, mean_rec, sigma_rec):
+    def write(self, offset, mean_rec, sigma_rec):  # pragma: no cover
         """mean_rec / sigma_rec [n,lat,lon]; entries under meandata.mask get the fill value
         (:288-291)."""
         n = mean_rec.shape[0]
         m = np.broadcast_to(self.mask, mean_rec.shape)
-        a = np.where(m, self.fill, np.asarray(mean_rec, dtype="f4"))
-        b = np.where(m, self.fill, np.asarray(sigma_rec, dtype="f4"))
-        self.v_mean[offset:offset + n] = a
-        self.v_sigma[offset:offset + n] = b
+        self.v_mean[offset:offset + n] = np.ma.masked_array(np.asarray(mean_rec, dtype="f4"), m)
+        self.v_sigma[offset:offset + n] = np.ma.masked_array(np.asarray(sigma_rec, dtype="f4"), m)
 
-    def close(self):
+    def write_records(self, offset, records, n=None):  # pragma: no cover
+        rec = np.frombuffer(memoryview(records).cast("B"), dtype=">f4").reshape(
+            -1, 2, self.mask.shape[0], self.mask.shape[1])
+        n = rec.shape[0] if n is None else n
+        m = np.broadcast_to(self.mask, (n,) + self.mask.shape)
+        self.v_mean[offset:offset + n] = np.ma.masked_array(rec[:n, 0].astype("f4"), m)
+        self.v_sigma[offset:offset + n] = np.ma.masked_array(rec[:n, 1].astype("f4"), m)
+
+    def close(self):  # pragma: no cover
         if self.ds is not None:
             self.ds.close()
             self.ds = None

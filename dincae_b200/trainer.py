@@ -183,7 +183,11 @@ class Reconstructor:
     """Forward-only sweep (DINCAE/__init__.py:678-689): test-mode batches, head, D2H."""
 
     def __init__(self, plan, cube, batch_size, net=None, train_mode_inputs=False, noise_seed=0,
-                 use_graph=True, py_random=None, jitter_std=None):
+                 use_graph=True, py_random=None, jitter_std=None, records=None, n_out_slots=2):
+        """``records=(meandata, fill_value)``: ``run_batch`` returns file-ready records
+        (big-endian float32 [B][2][H][W]: mean_rec = m_rec + meandata, sigma_rec, fill where
+        ``meandata`` is masked) instead of (m_rec, sigma2_rec) -- the per-batch arithmetic of
+        ``savesample`` runs on the device (``dincae_head_recon_records``)."""
         self.plan, self.cube, self.B = plan, cube, int(batch_size)
         self.net = net if net is not None else Network(plan, self.B, train=False, device=cube.dev)
         self.train_mode_inputs = train_mode_inputs       # reference quirk Q1
@@ -197,8 +201,21 @@ class Reconstructor:
         self._idx_events = [None] * len(self._idx_ring)
         self._idx_pos = 0
         self.idx_dev = torch.zeros(4 * B, dtype=torch.int32, device=dev)
-        self.out_host = [torch.zeros(2, B, plan.H, plan.W).pin_memory() for _ in range(2)]
-        self.out_dev = torch.zeros(2, B, plan.H, plan.W, device=dev)
+        self.records = records is not None
+        if self.records:
+            md = np.ma.asarray(records[0])
+            self._fill = float(records[1])
+            self._mean_is_f32 = md.dtype == np.float32
+            self._mean_dev = torch.from_numpy(
+                np.ascontiguousarray(np.ma.filled(md, 0).reshape(plan.H, plan.W), dtype=np.float64)).to(dev)
+            self._never_dev = torch.from_numpy(
+                np.ascontiguousarray(np.ma.getmaskarray(md).reshape(plan.H, plan.W)).view(np.uint8)).to(dev)
+            self.out_host = [torch.zeros(B, 2, plan.H, plan.W, dtype=torch.int32).pin_memory()
+                             for _ in range(n_out_slots)]
+            self.out_dev = torch.zeros(B, 2, plan.H, plan.W, dtype=torch.int32, device=dev)
+        else:
+            self.out_host = [torch.zeros(2, B, plan.H, plan.W).pin_memory() for _ in range(n_out_slots)]
+            self.out_dev = torch.zeros(2, B, plan.H, plan.W, device=dev)
         self._graphs = {}
         self._seq = 0
 
@@ -209,13 +226,18 @@ class Reconstructor:
         self.cube.build_batch(self.idx_dev[:B], cloud, n, net.X[0], net.xtrue, net.n_noncloud,
                               jitter_std=self.jitter_std, seed=self.noise_seed, noise_seq=self.idx_dev[2 * B:].view(torch.int64))
         net.forward(n, save_signs=False)
+        if self.records:
+            net.head_recon_records(n, self._mean_dev, self._never_dev, self._fill, self._mean_is_f32,
+                                   self.out_dev)
+            return
         net.head_recon(n)
         self.out_dev[0, :n].copy_(net.m_rec[:n])
         self.out_dev[1, :n].copy_(net.s2_rec[:n])
 
     def run_batch(self, frames, slot=0):
         """frames: int array (n <= B).  Returns pinned host tensor [2,B,H,W] (valid after a
-        stream sync): [0] = m_rec, [1] = sigma2_rec."""
+        stream sync): [0] = m_rec, [1] = sigma2_rec -- or, in records mode, the int32 view of
+        the big-endian float32 records [B,2,H,W]."""
         n, B = len(frames), self.B
         islot = self._idx_pos % len(self._idx_ring)
         self._idx_pos += 1
@@ -252,5 +274,8 @@ class Reconstructor:
         else:
             self._enqueue(n)
         out = self.out_host[slot]
-        out.copy_(self.out_dev, non_blocking=True)
+        if self.records:
+            out[:n].copy_(self.out_dev[:n], non_blocking=True)
+        else:
+            out.copy_(self.out_dev, non_blocking=True)
         return out

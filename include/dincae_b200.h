@@ -175,14 +175,15 @@ int dincae_head_recon(const float* xrec, int B, int H, int W,
 
 /* Head fused with the per-batch arithmetic of `savesample` (DINCAE/__init__.py:237-248,
  * 288-291), emitted as the records of the output file: records[b] = [mean_rec[b][H][W] |
- * sigma_rec[b][H][W]] float32 with mean_rec = float32(float64(m_rec) + meandata[H][W]),
- * sigma_rec = sqrt(sigma2_rec), both = fill_value where never[H][W] != 0 (meandata.mask;
- * NULL: nothing masked).  big_endian != 0 stores every value byte-reversed: the buffer is
+ * sigma_rec[b][H][W]] float32 with mean_rec = float32(float64(m_rec) + meandata[H][W])
+ * (mean_is_f32 != 0: the float32 sum m_rec + float32(meandata), numpy's result type when the
+ * input had no mask), sigma_rec = sqrt(sigma2_rec), both = fill_value where
+ * never[H][W] != 0 (meandata.mask; NULL: nothing masked).  big_endian != 0 stores every value byte-reversed: the buffer is
  * then the byte image of NetCDF-3 records (time-major, the two record variables
  * interleaved) and goes to the file with one write.  Identity output transform only. */
 int dincae_head_recon_records(const float* xrec, int B, int H, int W, const double* meandata,
-                              const uint8_t* never, float fill_value, int big_endian,
-                              void* records, void* stream);
+                              const uint8_t* never, float fill_value, int mean_is_f32,
+                              int big_endian, void* records, void* stream);
 
 /* Masked Gaussian NLL (or its truth_uncertain KL variant), RMS and the gradient w.r.t.
  * the last conv's pre-activation, DINCAE/__init__.py:520-570 and their TF gradients.

@@ -156,3 +156,40 @@ def test_clip_and_tf_adam(n, n_decay, beta, clip):
     torch.cuda.synchronize()
     want = 0.5 * float((torch.cat(params)[:n_decay].double() ** 2).sum())
     assert abs(out.item() - want) < 1e-5 * want
+
+
+@pytest.mark.parametrize("mean_f32,big_endian", [(0, 1), (1, 1), (0, 0)])
+def test_head_recon_records_equals_head_recon_plus_savesample(mean_f32, big_endian):
+    """dincae_head_recon_records == dincae_head_recon followed by the numpy arithmetic of
+    savesample (DINCAE/__init__.py:237-248, 288-291), BIT-EXACT, as NetCDF-3 record bytes."""
+    from dincae_b200 import _lib
+    from dincae_b200._lib import check, ptr
+    lib = _lib.load()
+    rs = np.random.RandomState(3 + mean_f32)
+    B, H, W = 3, 9, 14
+    xrec = torch.from_numpy(rs.standard_normal((B, 1, H, W, 4)).astype("f4") * 3).cuda()
+    md = (rs.standard_normal((H, W)) * 5 + 15)
+    md = md.astype("f4") if mean_f32 else md
+    never = rs.uniform(size=(H, W)) < 0.2
+    mr = torch.zeros(B, H, W, device="cuda")
+    sr = torch.zeros(B, H, W, device="cuda")
+    check(lib.dincae_head_recon(ptr(xrec), B, H, W, ptr(mr), ptr(sr), stream()))
+    rec = torch.zeros(B, 2, H, W, dtype=torch.int32, device="cuda")
+    md_dev = torch.from_numpy(md.astype("f8")).cuda()
+    nv_dev = torch.from_numpy(never.view(np.uint8)).cuda()
+    check(lib.dincae_head_recon_records(ptr(xrec), B, H, W, ptr(md_dev), ptr(nv_dev), -9999.0, mean_f32,
+                                        big_endian, ptr(rec), stream()))
+    torch.cuda.synchronize()
+    got = rec.cpu().numpy().view(">f4" if big_endian else "<f4")
+    want_mean = (mr.cpu().numpy() + md[None]).astype("f4")       # numpy result type: f8 or f4
+    want_sigma = np.sqrt(sr.cpu().numpy())
+    want_mean[:, never] = -9999.0
+    want_sigma[:, never] = -9999.0
+    assert np.array_equal(got[:, 0].astype("f4").view(np.uint32), want_mean.view(np.uint32))
+    assert np.array_equal(got[:, 1].astype("f4").view(np.uint32), want_sigma.view(np.uint32))
+    # no mask at all
+    check(lib.dincae_head_recon_records(ptr(xrec), B, H, W, ptr(md_dev), None, -9999.0, mean_f32,
+                                        big_endian, ptr(rec), stream()))
+    torch.cuda.synchronize()
+    got = rec.cpu().numpy().view(">f4" if big_endian else "<f4")
+    assert np.array_equal(got[:, 1].astype("f4"), np.sqrt(sr.cpu().numpy()))

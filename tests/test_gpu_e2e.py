@@ -78,6 +78,34 @@ def test_reconstruct_gridded_files_learns(small_example, tmp_path):
     assert np.sqrt(np.mean(err ** 2)) < 2.5             # reconstructs observed pixels (sigma of field ~4)
 
 
+def test_device_records_path_writes_the_same_file_as_the_savesample_hook(small_example, tmp_path):
+    """Stock savesample + identity transform = records emitted by the device and written by
+    threads; any other hook gets (m_rec, sigma2_rec) on the host like in the reference.  Same
+    seed, same (bit-deterministic) training: the two files must hold identical values."""
+    import DINCAE
+    from dincae_b200 import ncio
+    filename, varname, _ = small_example
+    calls = []
+
+    def hook(fname, m_rec, s2_rec, *args, **kw):
+        calls.append((m_rec.shape, args[4], args[5]))            # e, ii
+        return DINCAE.savesample(fname, m_rec, s2_rec, *args, **kw)
+
+    out = []
+    for k, kw in enumerate([{}, {"savesample": hook}]):
+        fname = DINCAE.reconstruct_gridded_files(
+            [{"filename": filename, "varname": varname}], str(tmp_path / ("r%d" % k)), iseed=4321,
+            epochs=2, save_each=1, batch_size=16, **kw)
+        out.append(ncio.read_recon(fname))
+    assert [c[0][0] for c in calls] == [16, 16, 16, 12] * 2      # ragged last batch, 2 sweeps
+    a, b = out
+    assert a["dims"] == b["dims"] and a["mean_rec"].shape == (60, 40, 48)
+    for k in ("lon", "lat", "meandata", "mean_rec", "sigma_rec"):
+        assert a[k + "_dims"] == b[k + "_dims"] and a[k + "_dtype"] == b[k + "_dtype"]
+        assert np.array_equal(np.ma.getmaskarray(a[k]), np.ma.getmaskarray(b[k])), k
+        assert np.array_equal(np.ma.getdata(a[k]).view(np.uint32), np.ma.getdata(b[k]).view(np.uint32)), k
+
+
 def test_user_generators_take_the_host_feed_path(tmp_path):
     """Arbitrary generator functions (not made by this package) still train (:399-410)."""
     import DINCAE

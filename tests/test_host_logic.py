@@ -245,3 +245,54 @@ def test_same_buffer_sees_through_fresh_mask_views():
     assert not _same_buffer(m[1:], m[:-1])
     assert not _same_buffer(m.view(np.uint8), m)
     assert not _same_buffer([True], m)
+
+
+def test_record_file_writer_is_a_valid_netcdf3_file(tmp_path):
+    """The streaming writer's bytes against an independent reader (scipy.io.netcdf_file):
+    dimensions, variables, dtypes, fill attributes, record interleaving, out-of-order and
+    threaded batch writes, append mode (DINCAE/__init__.py:251-294 layout)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from scipy.io import netcdf_file
+    from dincae_b200 import ncio
+    rs = np.random.RandomState(0)
+    H, W, T, B = 7, 10, 23, 5
+    lon, lat = np.linspace(-7, 0, W), np.linspace(33, 40, H)
+    md = np.ma.masked_array(rs.rand(1, H, W), rs.rand(1, H, W) < 0.3)
+    M = rs.standard_normal((T, H, W)).astype("f4")
+    S = rs.rand(T, H, W).astype("f4")
+    fname = str(tmp_path / "o.nc")
+    w = ncio.RecordFileWriter(fname, lon, lat, md)
+    batches = [(o, min(B, T - o)) for o in range(0, T, B)]
+    with ThreadPoolExecutor(3) as pool:                       # any order, several threads
+        for o, n in reversed(batches[:-1]):
+            pool.submit(w.write, o, M[o:o + n], S[o:o + n])
+    w.close()
+    with netcdf_file(fname, "r", mmap=False) as ds:
+        assert ds.version_byte == 2
+        assert list(ds.dimensions.items()) == [("time", None), ("lon", W), ("lat", H)]
+        assert ds.variables["mean_rec"].shape == (20, H, W)
+    o, n = batches[-1]                                        # re-open like savesample(ii > 0) does
+    w = ncio.RecordFileWriter(fname, lon, lat, md, append=True)
+    rec = np.empty((n, 2, H, W), ">f4")
+    rec[:, 0], rec[:, 1] = M[o:], S[o:]
+    rec[:, :, np.ma.getmaskarray(md)[0]] = -9999.0
+    w.write_records(o, rec.view(np.uint8).reshape(-1))
+    w.close()
+    with netcdf_file(fname, "r", mmap=False) as ds:
+        for k in ("meandata", "mean_rec", "sigma_rec"):
+            v = ds.variables[k]
+            assert v.typecode() == "f" and v._FillValue == np.float32(-9999.0)
+        assert ds.variables["mean_rec"].dimensions == ("time", "lat", "lon")
+        assert ds.variables["meandata"].dimensions == ("lat", "lon")
+        assert np.allclose(ds.variables["lon"][:], lon) and np.allclose(ds.variables["lat"][:], lat)
+        mask = np.ma.getmaskarray(md)[0]
+        for name, want in (("mean_rec", M), ("sigma_rec", S)):
+            got = np.array(ds.variables[name][:])
+            assert got.shape == (T, H, W)
+            assert np.array_equal(got[:, ~mask], want[:, ~mask])
+            assert np.all(got[:, mask] == -9999.0)
+        got = np.array(ds.variables["meandata"][:])
+        assert np.array_equal(got[~mask], np.ma.getdata(md)[0][~mask].astype("f4"))
+        assert np.all(got[mask] == -9999.0)
+    with pytest.raises(ValueError):                           # another grid: not appendable
+        ncio.RecordFileWriter(fname, lon[:-1], lat, md[:, :, :-1], append=True)
