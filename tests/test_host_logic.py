@@ -296,3 +296,17 @@ def test_record_file_writer_is_a_valid_netcdf3_file(tmp_path):
         assert np.all(got[mask] == -9999.0)
     with pytest.raises(ValueError):                           # another grid: not appendable
         ncio.RecordFileWriter(fname, lon[:-1], lat, md[:, :, :-1], append=True)
+
+
+def test_sampler_cloud_draws_are_randrange_draws():
+    """The sampler inlines random.randrange's rejection loop; it must consume and produce the
+    same stream as the call the reference makes (DINCAE/__init__.py:214)."""
+    import random
+    from dincae_b200 import sampler
+    for T in (1, 2, 7, 64, 100, 5266):
+        r1, r2 = random.Random(5), random.Random(5)
+        s = sampler.TrainSampler(T, 6, shuffle_buffer_size=1, seed=0, py_random=r1)
+        got = np.concatenate([s.next_batch()[1] for _ in range(20)])
+        want = [r2.randrange(0, T) for _ in range(len(got) + 1)]       # +1: the refill after the last pick
+        assert list(got) == want[:len(got)]
+        assert r1.random() == r2.random()                               # streams stay aligned
