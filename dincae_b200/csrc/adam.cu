@@ -14,7 +14,7 @@ struct RedWork {
 
 static int red_blocks(size_t n) {
   size_t b = (n + 4095) / 4096;
-  if (b > 2 * 148) b = 2 * 148;
+  if (b > 8 * 148) b = 8 * 148;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -35,8 +35,24 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ p,
   if (MODE == 0 && denom) grad_scale /= (float)(*denom);
   const bool decay = MODE == 0 && l2_beta != 0.f;
   const size_t n4 = n >> 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (size_t)gridDim.x * blockDim.x) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (!decay) {
+    // plain sum of squares of one array: four independent 16-byte loads in flight per thread
+    const float4* src = reinterpret_cast<const float4*>(MODE == 0 ? g : p);
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (; i0 + 3 * stride < n4; i0 += 4 * stride) {
+      const float4 a0 = __ldg(src + i0), a1 = __ldg(src + i0 + stride);
+      const float4 a2 = __ldg(src + i0 + 2 * stride), a3 = __ldg(src + i0 + 3 * stride);
+      s = f4_dot(a0, a0, s);
+      s1 = f4_dot(a1, a1, s1);
+      s2 = f4_dot(a2, a2, s2);
+      s3 = f4_dot(a3, a3, s3);
+    }
+    s = (s + s1) + (s2 + s3);
+    if (MODE == 0) s *= grad_scale * grad_scale;
+  }
+  for (size_t i = i0; i < n4; i += stride) {
     float4 a;
     if (MODE == 0) {
       a = f4_scale(__ldg(reinterpret_cast<const float4*>(g) + i), grad_scale);
@@ -125,12 +141,8 @@ __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p,
   const float scale = state[4];
   const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
   const size_t n4 = n >> 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = reinterpret_cast<const float4*>(g)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
+  const bool decay = l2_beta != 0.f;
+  auto update = [&](size_t i, float4& pp, const float4& gg, float4& mm, float4& vv) {
     float pa[4] = {pp.x, pp.y, pp.z, pp.w};
     const float ga[4] = {gg.x, gg.y, gg.z, gg.w};
     float ma[4] = {mm.x, mm.y, mm.z, mm.w};
@@ -138,15 +150,40 @@ __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ p,
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float gk = ga[k] * grad_scale;
-      if (4 * i + k < n_decay && l2_beta != 0.f) gk = fmaf(l2_beta, pa[k], gk);
+      if (decay && 4 * i + k < n_decay) gk = fmaf(l2_beta, pa[k], gk);
       gk *= scale;
       ma[k] = ma[k] + (gk - ma[k]) * omb1;
       va[k] = va[k] + (gk * gk - va[k]) * omb2;
       pa[k] = pa[k] - (ma[k] * lr_t) / (sqrtf(va[k]) + eps);
     }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    pp = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    mm = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    vv = make_float4(va[0], va[1], va[2], va[3]);
+  };
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // two elements per trip: all eight 16-byte loads are issued before the first store
+  for (; i + stride < n4; i += 2 * stride) {
+    const size_t j = i + stride;
+    float4 pa = p4[i], pb = p4[j];
+    const float4 ga = __ldg(g4 + i), gb = __ldg(g4 + j);
+    float4 ma = m4[i], mb = m4[j];
+    float4 va = v4[i], vb = v4[j];
+    update(i, pa, ga, ma, va);
+    update(j, pb, gb, mb, vb);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+    p4[j] = pb; m4[j] = mb; v4[j] = vb;
+  }
+  if (i < n4) {
+    float4 pa = p4[i];
+    const float4 ga = __ldg(g4 + i);
+    float4 ma = m4[i], va = v4[i];
+    update(i, pa, ga, ma, va);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
   }
   // tail (n not a multiple of 4)
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {

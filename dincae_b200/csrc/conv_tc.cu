@@ -45,14 +45,14 @@ constexpr int TC_KC = 2;                      // planes per stage (one K=8 MMA p
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_A_ROWS = TC_KC * TC_IN_ROWS;
 constexpr int TC_ROWS_PER_WARP = (TC_A_ROWS + TC_LOAD_WARPS - 1) / TC_LOAD_WARPS;
-constexpr int TC_MAX_N = 96;                  // widest MMA N (output channels, padded to 16)
+constexpr int TC_MAX_N = 256;                 // widest MMA N (output channels, padded to 16)
 constexpr int TC_WB = 4;                      // weight float4 per loader thread and pass
 
 struct TcPlan {
   int Xb, tiles_x, rbk, n_tiles, PWs, n_chunks, Nmma, n_stages, acc_cols, tmem_cols;
   int plane_elems;                            // smem plane stride of the A block (float4, 128-byte multiple)
   int a_elems, w_elems, stage_elems;          // float4 units
-  int w_div;                                  // 16.16 reciprocal for the weight index split
+  unsigned w_div;                             // ceil(2^32 / d): idx / d == __umulhi(idx, w_div) for idx < 2^16
   int tma0, tma1;                             // source 0 / source 1 planes arrive by TMA
 };
 
@@ -69,7 +69,7 @@ __device__ __forceinline__ void tc_load_w(float4 (&wv)[TC_WB], int base, int tid
   for (int u = 0; u < TC_WB; ++u) {
     const int idx = base + tid + u * LT;
     if (MODE == 0) {
-      const int q = (idx * L.w_div) >> 16;                // idx / Nmma
+      const int q = (int)__umulhi((unsigned)idx, L.w_div);   // idx / Nmma
       const int n = idx - q * L.Nmma;
       const int pl = q & (TC_KC - 1), tap = q >> 1;
       const bool ok = idx < L.w_elems && k0 + pl < Kp && n < P.out_planes * 4;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void tc_load_w(float4 (&wv)[TC_WB], int base, int tid
     } else {
       const int col = idx & (4 * TC_KC - 1);
       const int q = idx >> 3;
-      const int tap = (q * L.w_div) >> 16;                // q / (Nmma / 4)
+      const int tap = (int)__umulhi((unsigned)q, L.w_div);   // q / (Nmma / 4)
       const int cip = q - tap * (L.Nmma >> 2);
       const int co = 4 * k0 + col;
       const bool ok = idx < L.w_elems && cip < P.out_planes && co < Kp * 4 && co < P.cout_pad;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void tc_store_w(const float4 (&wv)[TC_WB], int base, 
     } else {
       const int col = idx & (4 * TC_KC - 1);
       const int q = idx >> 3;
-      const int tap = (q * L.w_div) >> 16;
+      const int tap = (int)__umulhi((unsigned)q, L.w_div);
       const int cip = q - tap * (L.Nmma >> 2);
       float* d = reinterpret_cast<float*>(Ws) + ((tap * TC_KC + (col >> 2)) * L.Nmma + 4 * cip) * 4 + (col & 3);
       d[0] = t.x; d[4] = t.y; d[8] = t.z; d[12] = t.w;
@@ -592,7 +592,10 @@ bool conv_tc_plan(int mode, int Kp, int out_planes, int B, int H, int W, TcPlan&
   L.plane_elems = (TC_IN_ROWS * L.PWs + 7) / 8 * 8;
   L.a_elems = TC_KC * L.plane_elems;
   L.w_elems = 9 * TC_KC * L.Nmma;
-  L.w_div = mode == 0 ? (65536 + L.Nmma - 1) / L.Nmma : (65536 + L.Nmma / 4 - 1) / (L.Nmma / 4);
+  {
+    const unsigned d = mode == 0 ? (unsigned)L.Nmma : (unsigned)(L.Nmma / 4);
+    L.w_div = (unsigned)((0x100000000ull + d - 1) / d);
+  }
   L.stage_elems = (L.a_elems + L.w_elems + 7) / 8 * 8;
   int ns = (200 * 1024) / (L.stage_elems * 16);
   if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;

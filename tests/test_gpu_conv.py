@@ -48,8 +48,9 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# the last two are BASELINE configs[3] widths (encoder [32,48,72,108,162]): MMA N of 112 / 176
 ENC_CASES = [(2, 12, 20, 10, 16), (3, 15, 11, 16, 24), (2, 7, 7, 36, 54), (1, 112, 112, 10, 16),
-             (2, 33, 70, 5, 3)]
+             (2, 33, 70, 5, 3), (1, 20, 24, 72, 108), (1, 18, 16, 108, 162)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", ENC_CASES)
@@ -124,7 +125,10 @@ def test_encoder_stage_forward_and_backward(B, H, W, Cin, Cout, backend):
 
 
 DEC_CASES = [(2, 14, 14, 54, 36, 36, True), (3, 15, 11, 24, 16, 16, True), (2, 28, 28, 36, 24, 24, False),
-             (1, 112, 112, 16, 10, 2, True), (2, 7, 9, 6, 0, 5, True)]
+             (1, 112, 112, 16, 10, 2, True), (2, 7, 9, 6, 0, 5, True),
+             # configs[3] decoder widths: 180 -> 72 (data-gradient N = 192), 270 -> 108 (N = 272:
+             # wider than one MMA, FFMA path)
+             (1, 18, 16, 108, 72, 72, True), (1, 16, 24, 162, 108, 108, True)]
 
 
 @pytest.mark.parametrize("B,H,W,C0,C1,Cout,want_skip_grad", DEC_CASES)

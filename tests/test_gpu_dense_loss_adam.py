@@ -29,7 +29,11 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-@pytest.mark.parametrize("B,K,N", [(50, 2744, 532), (3, 70, 33), (64, 128, 64), (130, 257, 19)])
+# batches <= 16 with K, N % 4 == 0 take the weight-streaming ("skinny") kernels: multi-split
+# partials, single-split fused epilogues, 8- and 16-row register tiles, ragged edges
+@pytest.mark.parametrize("B,K,N", [(50, 2744, 532), (3, 70, 33), (64, 128, 64), (130, 257, 19),
+                                   (8, 2744, 532), (13, 1000, 4100), (4, 64, 520), (16, 300, 1028),
+                                   (1, 128, 128), (9, 4, 4)])
 def test_dense_forward_backward(B, K, N):
     lib = _lib.load()
     g = torch.Generator().manual_seed(B + K + N)

@@ -46,15 +46,22 @@ def run(cube, plan, params, frames, clouds, seq, backward=True):
 
 def test_frames_are_independent_of_their_batch(setup):
     """A frame's reconstruction does not depend on which batch (or batch size) it is in: the
-    50-frame batch equals the same frames pushed through in batches of 17 -- bit for bit."""
+    50-frame batch equals the same frames pushed through in batches of 17 -- bit for bit.
+    Batches of 16 or fewer take the weight-streaming dense kernels (another summation order in
+    the bottleneck): bit-identical among themselves, rounding-level agreement with the rest."""
     cube, plan, params, frames, clouds, seq = setup
     full = run(cube, plan, params, frames, clouds, seq, backward=False)
     m_full, s_full = full.m_rec.cpu().numpy(), full.s2_rec.cpu().numpy()
-    for lo in range(0, B, 17):
-        hi = min(B, lo + 17)
+    for lo, hi in ((0, 17), (17, 34), (33, 50)):
         part = run(cube, plan, params, frames[lo:hi], clouds[lo:hi], seq[lo:hi], backward=False)
         assert np.array_equal(part.m_rec.cpu().numpy(), m_full[lo:hi])
         assert np.array_equal(part.s2_rec.cpu().numpy(), s_full[lo:hi])
+    small = [run(cube, plan, params, frames[:n], clouds[:n], seq[:n], backward=False) for n in (5, 8, 13, 16)]
+    for net in small[1:]:
+        assert np.array_equal(net.m_rec.cpu().numpy()[:5], small[0].m_rec.cpu().numpy())
+        assert np.array_equal(net.s2_rec.cpu().numpy()[:5], small[0].s2_rec.cpu().numpy())
+    m16 = small[-1].m_rec.cpu().numpy()
+    assert np.abs(m16 - m_full[:16]).max() <= 2e-3 * np.abs(m_full).max()    # TF32 conv back end
     assert np.isfinite(m_full).all() and (s_full > 0).all()
 
 

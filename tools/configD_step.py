@@ -31,3 +31,36 @@ o = rec.run_batch(np.arange(B))
 torch.cuda.synchronize()
 print("recon finite:", bool(torch.isfinite(o).all()), "params", plan.n_params_tf,
       "GB allocated %.1f" % (torch.cuda.max_memory_allocated() / 1e9))
+
+# ---- per-call breakdown of one training step (eager, CUDA events; side stream serialised) ------
+from dincae_b200 import _lib
+records = []
+
+
+def tracer(label, fn, args, nbytes, nflops):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), label)
+    e1.record()
+    records.append((label, e0, e1, nbytes, nflops))
+
+
+tr.net.tracer = tracer
+reps = 3
+for _ in range(reps):
+    tr.net.n_noncloud.zero_()
+    torch.cuda._sleep(20_000_000)
+    tr.net.forward(B)
+    tr.net.loss_backward(B, False, normalise=False)
+    tr.net.adam_step(denom=tr.net.loss_sums[3:4])
+    torch.cuda.synchronize()
+tr.net.tracer = None
+agg = {}
+for label, e0, e1, nb, nf in records:
+    d = agg.setdefault(label, [0.0, nb, nf])
+    d[0] += e0.elapsed_time(e1) / reps
+tot = sum(v[0] for v in agg.values())
+print("B=%d  sum of calls %.2f ms" % (B, tot))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print("%8.3f ms  %5.1f%%  %7.1f GB/s alg  %7.2f TFLOP/s alg  %s" % (
+        v[0], 100 * v[0] / tot, v[1] / v[0] / 1e6, v[2] / v[0] / 1e9, k))
