@@ -33,6 +33,7 @@ SIGNATURES = {
     "dincae_conv3x3_dgrad": (c_int, [vp, vp, vp, c_float, c_int, vp, c_int, c_int, c_int, c_int,
                                      c_int, c_int, vp, c_float, vp, c_int, vp, vp, vp]),
     "dincae_conv3x3_wgrad_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "dincae_conv3x3_wgrad_on_tensor_cores": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "dincae_conv3x3_wgrad": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
                                      c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]),
     "dincae_conv3x3_wgrad_partial": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,

@@ -44,6 +44,7 @@ struct WgTcParams {
   float* partial;           // [gridDim.x][wsize + cout_pad]
   // plan
   int R, TW, n_row_blocks, n_tiles;
+  int tiles_x, TWt, x_off;  // tiles per image row; image columns per tile; tile column of its first own pixel
   int cgu, cgg;             // channel groups (of 8) of U (incl. ones row) and of one G copy
   int M, N, ones_row;
   int npg_u, npg_g;         // pixel groups (of 4) in the U / G tile
@@ -65,6 +66,16 @@ struct WgPass {
   int tile, it;
 };
 
+// tile -> image, first row, and the image column that tile column 0 stands for
+__device__ __forceinline__ void wg_tile(const WgTcParams& P, int tile, int& b, int& y0, int& x0) {
+  const int per_img = P.n_row_blocks * P.tiles_x;
+  b = tile / per_img;
+  const int rem = tile - b * per_img;
+  const int rb = rem / P.tiles_x;
+  y0 = rb * P.R;
+  x0 = (rem - rb * P.tiles_x) * P.TWt - P.x_off;
+}
+
 // next pass of a warp that takes items first, first + step, ... of every `tile_stride`-th tile
 __device__ __forceinline__ WgPass wg_next(WgPass c, int n_pad, int first, int step, int tile_stride) {
   c.it += step;
@@ -84,8 +95,8 @@ __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, i
   const unsigned e = on ? item_tab[c.it] : 0u;
   const int plane = (e >> 6) & 0x1ff, chunk = e & 63;
   const bool is_g = (e & 0x8000u) != 0;
-  const int b = c.tile / P.n_row_blocks;
-  const int y0 = (c.tile - b * P.n_row_blocks) * P.R;
+  int b, y0, x0;
+  wg_tile(P, c.tile, b, y0, x0);
   const ConvSrc& U = P.u;
   const ConvSrc& G = P.g;
   // plane base offsets (float4 units), resolved once per pass
@@ -104,15 +115,18 @@ __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, i
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int p = chunk * 128 + lane + 32 * u;
-    const int r = (int)__umulhi((unsigned)p, P.inv_tw), x = p - r * P.TW;
+    const int r = (int)__umulhi((unsigned)p, P.inv_tw), xt = p - r * P.TW;
+    const int x = x0 + xt;                        // image column (negative / >= W in the halo)
     sb[u] = 0;
     if (!is_g) {
       const int y = y0 - 1 + r;
-      const bool ok = on && p < npix && (unsigned)y < (unsigned)P.H && x < P.W;
+      const bool ok = on && p < npix && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W;
       v[u] = ldg_f4_pred(ubase + ((y >> ush) * uw + (x >> ush)), ok);
     } else {
+      // a tile takes the gradient of its own TWt columns only (the halo columns stay zero), so
+      // that every pixel of G enters the sum exactly once
       const int y = y0 + r;
-      const bool ok = on && p < npix && y < P.H && x < P.W;
+      const bool ok = on && p < npix && y < P.H && xt >= P.x_off && xt < P.x_off + P.TWt && x < P.W;
       if (GMODE == 0) {
         v[u] = ldg_f4_pred(gbase + (y * G.W + x), ok);
       } else {
@@ -135,8 +149,8 @@ __device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, 
   const int TW = P.TW;
   float* Ut = stage;
   float* Gt = stage + P.u_floats;
-  const int b = c.tile / P.n_row_blocks;
-  const int y0 = (c.tile - b * P.n_row_blocks) * P.R;
+  int b, y0, x0;
+  wg_tile(P, c.tile, b, y0, x0);
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int p = chunk * 128 + lane + 32 * u;
@@ -147,7 +161,7 @@ __device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, 
       float4 t = v[u];
       if (GMODE == 1) {
         const int y = y0 + r;
-        t = tc_unpool(t, sb[u], x, P.W, (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f, P.g.slope);
+        t = tc_unpool(t, sb[u], x0 + x, P.W, (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f, P.g.slope);
       }
       t = to_tf32(t);
       // copy dx holds G[x' - dx + 1] at column x', i.e. G[x] lands at column x + dx - 1 (the
@@ -374,8 +388,7 @@ static int wg_pow2_cols(int v) {
 // Shape plan; false when the layer does not fit this path (caller uses the FFMA kernel).
 bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
   const int Cin4 = 4 * P.kp;
-  if (P.W > 128 || P.kp > 31 || P.gp > 21) return false;
-  P.TW = (P.W + 7) / 8 * 8;
+  if (P.kp > 31 || P.gp > 21) return false;
   P.ones_row = Cin4;                                // first row after the packed channels
   P.cgu = (Cin4 + 1 + 7) / 8;
   P.cgg = (P.gp * 4 + 7) / 8;
@@ -392,14 +405,50 @@ bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
   P.pitch_u = (P.cgu * 9 + ((P.cgu & 1) ? 0 : 1)) * 4;
   P.pitch_g = (3 * P.cgg * 9 + (((3 * P.cgg) & 1) ? 0 : 1)) * 4;
   const int slack = 16 * WG_CM;                     // over-read of the unused MMA row groups
-  // rows per stage: largest R (<= 16) whose two stages fit in ~200 KB
-  int best = 0;
-  for (int R = 1; R <= 16 && R <= P.H; ++R) {
-    const long long uf = (long long)((R + 2) * P.TW / 4) * P.pitch_u + slack;
-    const long long gf = (long long)(R * P.TW / 4) * P.pitch_g + slack;
-    const int cu = ((R + 2) * P.TW + 127) / 128, cg = (R * P.TW + 127) / 128;
+  // Tile = R image rows x TWt image columns.  Up to 128 columns a tile spans the image width
+  // (no column halo: the three dx-shifted copies of G take care of the taps, and U is zero
+  // outside the image).  Wider images are cut into column tiles whose staged block carries 4
+  // halo columns on either side (a pixel group, so that K steps stay aligned): U is loaded for
+  // the whole block, G only for the tile's own columns.
+  auto fits = [&](int R, int TW) {
+    const long long uf = (long long)((R + 2) * TW / 4) * P.pitch_u + slack;
+    const long long gf = (long long)(R * TW / 4) * P.pitch_g + slack;
+    const int cu = ((R + 2) * TW + 127) / 128, cg = (R * TW + 127) / 128;
     const int items = P.kp * cu + P.gp * cg;
-    if ((uf + gf) * 4 * WG_STAGES <= 200 * 1024 && items <= WG_MAX_ITEMS && cu <= 63) best = R;
+    return (uf + gf) * 4 * WG_STAGES <= 200 * 1024 && items <= WG_MAX_ITEMS && cu <= 63;
+  };
+  int best = 0;
+  if (P.W <= 128) {
+    P.TW = (P.W + 7) / 8 * 8;
+    P.TWt = P.TW;
+    P.x_off = 0;
+    P.tiles_x = 1;
+    // rows per stage: largest R (<= 16) whose two stages fit in ~200 KB
+    for (int R = 1; R <= 16 && R <= P.H; ++R)
+      if (fits(R, P.TW)) best = R;
+  } else {
+    // the shape with the least staged traffic per useful pixel
+    double best_score = 0.0;
+    int best_twt = 0;
+    for (int twt = 32; twt <= 128; twt += 16) {
+      const int TW = twt + 8;
+      for (int R = 1; R <= 16 && R <= P.H; ++R) {
+        if (!fits(R, TW)) continue;
+        const double score = (double)R * twt * (P.kp + P.gp) /
+                             ((double)(R + 2) * TW * P.kp + (double)R * TW * P.gp);
+        if (score > best_score + 1e-9) {
+          best_score = score;
+          best = R;
+          best_twt = twt;
+        }
+      }
+    }
+    if (best) {
+      P.TWt = best_twt;
+      P.TW = best_twt + 8;
+      P.x_off = 4;
+      P.tiles_x = (P.W + best_twt - 1) / best_twt;
+    }
   }
   if (!best) return false;
   P.R = best;
@@ -414,7 +463,8 @@ bool conv_wgrad_tc_plan(WgTcParams& P, int sm_count) {
   P.n_items = P.n_items_u + P.gp * P.chunks_g;
   P.inv_tw = (unsigned)((0x100000000ull + P.TW - 1) / P.TW);
   P.n_row_blocks = (P.H + P.R - 1) / P.R;
-  P.n_tiles = P.B * P.n_row_blocks;
+  if ((long long)P.B * P.n_row_blocks * P.tiles_x > (1ll << 30)) return false;
+  P.n_tiles = P.B * P.n_row_blocks * P.tiles_x;
   (void)sm_count;
   return true;
 }
@@ -465,6 +515,13 @@ int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, 
 }
 
 }  // namespace dincae
+
+extern "C" int dincae_conv3x3_wgrad_on_tensor_cores(int cinp, int gp, int B, int H, int W) {
+  if (cinp <= 0 || gp <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  dincae::WgTcParams P = {};
+  P.B = B; P.H = H; P.W = W; P.kp = cinp; P.gp = gp;
+  return dincae::conv_wgrad_tc_plan(P, 148) ? 1 : 0;
+}
 
 #ifdef DINCAE_TC_TIMELINE
 extern "C" int dincae_debug_timeline_wg(long long* host_out, int reset) {

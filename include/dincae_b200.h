@@ -143,6 +143,10 @@ int dincae_conv3x3_dgrad(const float* g_full, const float* g_pool, const uint16_
  * db [cout_pad].  Deterministic two-stage reduction through `workspace`
  * (dincae_conv3x3_wgrad_workspace() bytes). */
 size_t dincae_conv3x3_wgrad_workspace(int c0p, int c1p, int cout_pad, int B, int H, int W);
+/* Diagnostic: 1 when a weight gradient of this shape (cinp = c0p + c1p input planes, gp gradient
+ * planes) runs on the tensor-core kernel under back end 1, 0 when it takes the FFMA kernel
+ * (shape outside the tcgen05 plan).  No device work. */
+int dincae_conv3x3_wgrad_on_tensor_cores(int cinp, int gp, int B, int H, int W);
 int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half,
                          const float* src1, int c1p,
                          const float* g_full, const float* g_pool, const uint16_t* sign,

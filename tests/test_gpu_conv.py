@@ -50,7 +50,9 @@ def stream():
 
 # the last two are BASELINE configs[3] widths (encoder [32,48,72,108,162]): MMA N of 112 / 176
 ENC_CASES = [(2, 12, 20, 10, 16), (3, 15, 11, 16, 24), (2, 7, 7, 36, 54), (1, 112, 112, 10, 16),
-             (2, 33, 70, 5, 3), (1, 20, 24, 72, 108), (1, 18, 16, 108, 162)]
+             (2, 33, 70, 5, 3), (1, 20, 24, 72, 108), (1, 18, 16, 108, 162),
+             # wider than 128 columns: the tensor-core weight gradient cuts rows into column tiles
+             (1, 20, 200, 10, 16), (2, 9, 131, 5, 3)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", ENC_CASES)
@@ -128,7 +130,8 @@ DEC_CASES = [(2, 14, 14, 54, 36, 36, True), (3, 15, 11, 24, 16, 16, True), (2, 2
              (1, 112, 112, 16, 10, 2, True), (2, 7, 9, 6, 0, 5, True),
              # configs[3] decoder widths: 180 -> 72 (data-gradient N = 192), 270 -> 108 (N = 272:
              # wider than one MMA, FFMA path)
-             (1, 18, 16, 108, 72, 72, True), (1, 16, 24, 162, 108, 108, True)]
+             (1, 18, 16, 108, 72, 72, True), (1, 16, 24, 162, 108, 108, True),
+             (1, 12, 160, 16, 10, 2, True), (1, 10, 258, 32, 28, 2, False)]
 
 
 @pytest.mark.parametrize("B,H,W,C0,C1,Cout,want_skip_grad", DEC_CASES)
@@ -256,3 +259,16 @@ def test_invalid_arguments_are_rejected():
                                   None, None, None, stream()) == -1
     assert lib.dincae_conv3x3_fwd(ptr(x), 1, 0, None, 0, ptr(x), ptr(x), 16, 1, 2, 2, 5, 0.2,
                                   ptr(x), None, None, stream()) == -1
+
+
+def test_wide_images_take_the_tensor_core_weight_gradient():
+    """Plan check (no device work): the column-tiled tcgen05 weight gradient covers the wide
+    parity cases above and the 512x512 / 256x256 layers of BASELINE configs[3]."""
+    lib = _lib.load()
+    on = lib.dincae_conv3x3_wgrad_on_tensor_cores
+    assert on(3, 4, 1, 20, 200) == 1 and on(2, 1, 2, 9, 131) == 1          # ENC_CASES (planes)
+    assert on(4 + 3, 1, 1, 12, 160) == 1 and on(8 + 7, 1, 1, 10, 258) == 1  # DEC_CASES
+    assert on(7, 8, 8, 512, 512) == 1 and on(8, 12, 8, 256, 256) == 1       # config D enc 1, enc 2
+    assert on(20, 8, 8, 256, 256) == 1 and on(15, 1, 8, 512, 512) == 1      # config D dec 4, dec 5
+    assert on(3, 4, 50, 112, 112) == 1                                      # config A enc 1
+    assert on(68, 27, 8, 32, 32) == 0                                       # 270 -> 108: FFMA kernel
