@@ -67,7 +67,15 @@ struct WgPass {
 };
 
 // tile -> image, first row, and the image column that tile column 0 stands for
+// (XT = 0: one tile spans the image width -- no column arithmetic in the loader's hot loop)
+template <int XT>
 __device__ __forceinline__ void wg_tile(const WgTcParams& P, int tile, int& b, int& y0, int& x0) {
+  if (XT == 0) {
+    b = tile / P.n_row_blocks;
+    y0 = (tile - b * P.n_row_blocks) * P.R;
+    x0 = 0;
+    return;
+  }
   const int per_img = P.n_row_blocks * P.tiles_x;
   b = tile / per_img;
   const int rem = tile - b * per_img;
@@ -88,7 +96,7 @@ __device__ __forceinline__ WgPass wg_next(WgPass c, int n_pad, int first, int st
 
 // Issue the 4 loads of one pass (item c.it of tile c.tile) of this lane.  All offsets are
 // 32-bit (the plan rejects tensors of 2^31 float4 or more).
-template <int GMODE>
+template <int GMODE, int XT>
 __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, int lane,
                                          const uint16_t* item_tab, float4 (&v)[4], unsigned (&sb)[4]) {
   const bool on = c.it < P.n_items;
@@ -96,7 +104,7 @@ __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, i
   const int plane = (e >> 6) & 0x1ff, chunk = e & 63;
   const bool is_g = (e & 0x8000u) != 0;
   int b, y0, x0;
-  wg_tile(P, c.tile, b, y0, x0);
+  wg_tile<XT>(P, c.tile, b, y0, x0);
   const ConvSrc& U = P.u;
   const ConvSrc& G = P.g;
   // plane base offsets (float4 units), resolved once per pass
@@ -126,7 +134,8 @@ __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, i
       // a tile takes the gradient of its own TWt columns only (the halo columns stay zero), so
       // that every pixel of G enters the sum exactly once
       const int y = y0 + r;
-      const bool ok = on && p < npix && y < P.H && xt >= P.x_off && xt < P.x_off + P.TWt && x < P.W;
+      const bool ok = on && p < npix && y < P.H && x < P.W &&
+                      (XT == 0 || (xt >= P.x_off && xt < P.x_off + P.TWt));
       if (GMODE == 0) {
         v[u] = ldg_f4_pred(gbase + (y * G.W + x), ok);
       } else {
@@ -138,7 +147,7 @@ __device__ __forceinline__ void wg_issue(const WgTcParams& P, const WgPass& c, i
 }
 
 // Convert (TF32) and store one pass into its stage: U transposed, G as three dx-shifted copies.
-template <int GMODE>
+template <int GMODE, int XT>
 __device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, int lane,
                                           const uint16_t* item_tab, float* stage,
                                           const float4 (&v)[4], const unsigned (&sb)[4]) {
@@ -150,7 +159,7 @@ __device__ __forceinline__ void wg_commit(const WgTcParams& P, const WgPass& c, 
   float* Ut = stage;
   float* Gt = stage + P.u_floats;
   int b, y0, x0;
-  wg_tile(P, c.tile, b, y0, x0);
+  wg_tile<XT>(P, c.tile, b, y0, x0);
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int p = chunk * 128 + lane + 32 * u;
@@ -182,7 +191,7 @@ __device__ long long wg_dbg[3 * 2048];
 #define WG_MARK(code)
 #endif
 
-template <int GMODE>
+template <int GMODE, int XT>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const WgTcParams P) {
 #ifdef DINCAE_TC_TIMELINE
   int wg_k[3] = {0, 0, 0};
@@ -255,16 +264,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
     float4 va[4], vb[4];
     unsigned sa[4], sbb[4];
     uint32_t ph = 0;
-    if (cur.tile < P.n_tiles) wg_issue<GMODE>(P, cur, lane, item_tab, va, sa);
+    if (cur.tile < P.n_tiles) wg_issue<GMODE, XT>(P, cur, lane, item_tab, va, sa);
     while (cur.tile < P.n_tiles) {
       // ---- pass A ---------------------------------------------------------------------------
       nxt = wg_next(cur, n_pad, wl, GW, tstride);
       bool last = nxt.tile != cur.tile;
-      if (!last) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
+      if (!last) wg_issue<GMODE, XT>(P, nxt, lane, item_tab, vb, sbb);
       if (warp == 0) WG_MARK(100);
       if (cur.it == wl) mbar_wait(&empty_bar[grp], ph ^ 1u);
       if (warp == 0) WG_MARK(101);
-      wg_commit<GMODE>(P, cur, lane, item_tab, stage, va, sa);
+      wg_commit<GMODE, XT>(P, cur, lane, item_tab, stage, va, sa);
       if (warp == 0) WG_MARK(102);
       if (last) {
         fence_async_smem();
@@ -272,18 +281,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
         if (lane == 0) mbar_arrive(&full_bar[grp]);
         if (warp == 0) WG_MARK(103);
         ph ^= 1u;
-        if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, vb, sbb);
+        if (nxt.tile < P.n_tiles) wg_issue<GMODE, XT>(P, nxt, lane, item_tab, vb, sbb);
       }
       cur = nxt;
       if (cur.tile >= P.n_tiles) break;
       // ---- pass B (buffers swapped) ------------------------------------------------------------
       nxt = wg_next(cur, n_pad, wl, GW, tstride);
       last = nxt.tile != cur.tile;
-      if (!last) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
+      if (!last) wg_issue<GMODE, XT>(P, nxt, lane, item_tab, va, sa);
       if (warp == 0) WG_MARK(100);
       if (cur.it == wl) mbar_wait(&empty_bar[grp], ph ^ 1u);
       if (warp == 0) WG_MARK(101);
-      wg_commit<GMODE>(P, cur, lane, item_tab, stage, vb, sbb);
+      wg_commit<GMODE, XT>(P, cur, lane, item_tab, stage, vb, sbb);
       if (warp == 0) WG_MARK(102);
       if (last) {
         fence_async_smem();
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tc_kernel(const W
         if (lane == 0) mbar_arrive(&full_bar[grp]);
         if (warp == 0) WG_MARK(103);
         ph ^= 1u;
-        if (nxt.tile < P.n_tiles) wg_issue<GMODE>(P, nxt, lane, item_tab, va, sa);
+        if (nxt.tile < P.n_tiles) wg_issue<GMODE, XT>(P, nxt, lane, item_tab, va, sa);
       }
       cur = nxt;
     }
@@ -497,19 +506,18 @@ int wgrad_tc(const ConvSrc& u, const ConvSrc& g, int B, int H, int W, int cinp, 
   const int nblk = wgrad_tc_blocks(P, sm_count);
   if ((size_t)nblk * ((size_t)P.wsize + cout_pad) * sizeof(float) > partial_bytes) return DINCAE_ENOSPC;
   const int gmode = g.mode;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[gmode]) {
-    cudaError_t e = gmode == 0
-        ? cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)
-        : cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+  const int xt = P.tiles_x > 1 ? 1 : 0;
+  void (*kern)(const WgTcParams) =
+      gmode == 0 ? (xt ? conv3x3_wgrad_tc_kernel<0, 1> : conv3x3_wgrad_tc_kernel<0, 0>)
+                 : (xt ? conv3x3_wgrad_tc_kernel<1, 1> : conv3x3_wgrad_tc_kernel<1, 0>);
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[2 * gmode + xt]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return cuda_rc(e);
-    attr_set[gmode] = true;
+    attr_set[2 * gmode + xt] = true;
   }
   const size_t smem = (size_t)WG_STAGES * P.stage_floats * 4;
-  if (gmode == 0)
-    launch_k(conv3x3_wgrad_tc_kernel<0>, nblk, WG_THREADS, smem, st, P);
-  else
-    launch_k(conv3x3_wgrad_tc_kernel<1>, nblk, WG_THREADS, smem, st, P);
+  launch_k(kern, nblk, WG_THREADS, smem, st, P);
   *nblk_out = nblk;
   return check_launch();
 }
