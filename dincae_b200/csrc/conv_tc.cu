@@ -450,11 +450,7 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
               for (int qq = 0; qq < 4; ++qq) wb[qq] |= __shfl_xor_sync(0xffffffffu, wb[qq], 2);
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq)
-#ifndef EXP_NOSTORE
                 if ((lane & 3) == 0 && valid && p0 + qq < P.out_planes)
-#else
-                if (wb[qq] == 0x12345u)
-#endif
                   P.out_sign[o_sign + (p0 + qq) * s_sign + 2 * j] = (uint16_t)wb[qq];
             }
             if (P.out_full) {
@@ -480,11 +476,7 @@ conv3x3_tc_kernel(const TcParams Q, const __grid_constant__ CUtensorMap tm0,
               }
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq)
-#ifndef EXP_NOSTORE
                 if (store_lane && valid && p0 + qq < P.out_planes)
-#else
-                if (a[qq].x == 1.2345f)
-#endif
                   P.out_pool[o_half + (p0 + qq) * s_half + 4 * j] = to_tf32(f4_scale(a[qq], pool_scale));
             }
           } else {
