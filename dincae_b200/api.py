@@ -358,7 +358,7 @@ def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size):
     import torch
     from concurrent.futures import ThreadPoolExecutor
     from .sampler import sequential_batches
-    writer = ncio.ReconWriter(fname, lon, lat, meandata)
+    writer = ncio.ReconWriter(fname, lon, lat, meandata, expect_records=test_len)
     nslots = len(recon.out_host)
 
     def put(ev, buf, offset, n):

@@ -261,12 +261,13 @@ def test_record_file_writer_is_a_valid_netcdf3_file(tmp_path):
     M = rs.standard_normal((T, H, W)).astype("f4")
     S = rs.rand(T, H, W).astype("f4")
     fname = str(tmp_path / "o.nc")
-    w = ncio.RecordFileWriter(fname, lon, lat, md)
+    w = ncio.RecordFileWriter(fname, lon, lat, md, expect_records=T + 9)      # over-estimate: trimmed on close
     batches = [(o, min(B, T - o)) for o in range(0, T, B)]
     with ThreadPoolExecutor(3) as pool:                       # any order, several threads
         for o, n in reversed(batches[:-1]):
             pool.submit(w.write, o, M[o:o + n], S[o:o + n])
     w.close()
+    assert os.path.getsize(fname) == w.rec_start + 20 * w.recsize
     with netcdf_file(fname, "r", mmap=False) as ds:
         assert ds.version_byte == 2
         assert list(ds.dimensions.items()) == [("time", None), ("lon", W), ("lat", H)]
