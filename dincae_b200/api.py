@@ -184,6 +184,19 @@ def _output_name(outdir):
     return os.path.join(outdir, "data-{}.nc".format(now.strftime("%Y-%m-%dT%H%M%S")))
 
 
+def _dp_context():
+    """(torch.distributed, rank, world) when the caller runs one process per GPU inside an
+    initialised process group of more than one rank (e.g. ``torchrun run_DINCAE.py`` after
+    ``init_process_group("nccl")`` and ``torch.cuda.set_device``), else (None, 0, 1)."""
+    try:
+        import torch.distributed as tdist
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+            return tdist, tdist.get_rank(), tdist.get_world_size()
+    except Exception:            # noqa: BLE001
+        pass
+    return None, 0, 1
+
+
 def reconstruct(lon, lat, mask, meandata,
                 train_datagen, train_len,
                 test_datagen, test_len,
@@ -219,6 +232,13 @@ def reconstruct(lon, lat, mask, meandata,
     accepted and ignored (dropout never fires in the reference; the feed is
     on the GPU); only nearest-neighbour ``resize_method`` exists; ``tensorboard`` writes
     scalars only when ``torch.utils.tensorboard`` is importable.
+
+    New capability: inside an initialised ``torch.distributed`` group
+    of N > 1 ranks (one process per GPU) training is data parallel -- every rank builds
+    ``batch_size`` frames of a global batch of N x ``batch_size`` drawn from one shared index
+    stream, gradients are all-reduced (an epoch is ceil(train_len / (N x batch_size)) steps) --
+    and the reconstruction sweep is sharded by time range into one output file.  Rank 0 prints,
+    saves checkpoints and TensorBoard scalars; every rank returns the same file name.
     """
     import torch
     from .engine import Plan
@@ -237,18 +257,35 @@ def reconstruct(lon, lat, mask, meandata,
         shuffle_seed = init_seed
         noise_seed = init_seed
 
-    print("regularization_L2_beta ", regularization_L2_beta)
-    print("enc_nfilter_internal ", enc_nfilter_internal)
-    print("nvar ", nvar)
-    print("nepoch_keep_missing ", nepoch_keep_missing)
+    dist, rank, world = _dp_context()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    py_random = None
+    if dist is not None:
+        # one shared index / noise / initialisation stream on every rank
+        box = [init_seed, shuffle_seed if shuffle_seed is not None else random.getrandbits(31),
+               noise_seed, None if iseed is not None else random.getrandbits(62)]
+        dist.broadcast_object_list(box, src=0)
+        init_seed, shuffle_seed, noise_seed = box[0], box[1], box[2]
+        if box[3] is not None:
+            py_random = random.Random(box[3])
 
-    if outdir is not None and not os.path.isdir(outdir):
+    say("regularization_L2_beta ", regularization_L2_beta)
+    say("enc_nfilter_internal ", enc_nfilter_internal)
+    say("nvar ", nvar)
+    say("nepoch_keep_missing ", nepoch_keep_missing)
+
+    if outdir is not None and not os.path.isdir(outdir) and rank == 0:
         os.mkdir(outdir)
+    if dist is not None:
+        dist.barrier()
 
     jmax, imax = mask.shape
     plan = Plan(jmax, imax, nvar, enc_nfilter_internal, frac_dense_layer, skipconnections)
 
     if not isinstance(train_datagen, FrameSource) or not isinstance(test_datagen, FrameSource):
+        if dist is not None:
+            raise ValueError("data-parallel runs need the generators of data_generator / "
+                             "data_generator_list (the batch is built on each rank's GPU)")
         from .hostfeed import reconstruct_from_generators
         return reconstruct_from_generators(
             plan, lon, lat, mask, meandata, train_datagen, train_len, test_datagen, test_len,
@@ -268,9 +305,11 @@ def reconstruct(lon, lat, mask, meandata,
     trainer = Trainer(plan, cube, batch_size, truth_uncertain=truth_uncertain,
                       clip_grad=clip_grad, l2_beta=regularization_L2_beta,
                       noise_seed=noise_seed, init_seed=init_seed,
-                      jitter_std=train_datagen.jitter_std)
-    sampler = TrainSampler(train_len, batch_size, shuffle_buffer_size, seed=shuffle_seed,
-                           train=train_datagen.train)
+                      jitter_std=train_datagen.jitter_std, dist_group=True if dist is not None else None)
+    sampler = TrainSampler(train_len, batch_size * world, shuffle_buffer_size, seed=shuffle_seed,
+                           py_random=py_random, train=train_datagen.train)
+    mine = slice(rank * batch_size, (rank + 1) * batch_size)
+    shard_sweep = dist is not None and not ncio.have_netcdf4()      # HDF5: single writer
     # With the stock `savesample` and no output transform the per-batch arithmetic of
     # savesample (:237-248, 288-291) runs on the device and the sweep hands file-ready records
     # to writer threads; any other hook / transform gets (m_rec, sigma2_rec) on the host like
@@ -282,7 +321,7 @@ def reconstruct(lon, lat, mask, meandata,
                           records=(meandata, -9999.) if fast_save else None,
                           n_out_slots=_SAVE_SLOTS if fast_save else 2)
     writer_tb = None
-    if tensorboard and outdir is not None:
+    if tensorboard and outdir is not None and rank == 0:
         try:
             from torch.utils.tensorboard import SummaryWriter
             writer_tb = SummaryWriter(os.path.join(outdir, "train"))
@@ -290,10 +329,10 @@ def reconstruct(lon, lat, mask, meandata,
             writer_tb = None
 
     dt_start = datetime.now()
-    print(dt_start)
+    say(dt_start)
     fname = None
     index = 0
-    steps_per_epoch = ceil(train_len / batch_size)
+    steps_per_epoch = ceil(train_len / (batch_size * world))
 
     def drain(e, first_step):
         nonlocal index
@@ -305,8 +344,8 @@ def reconstruct(lon, lat, mask, meandata,
             index += 1
             ii = first_step + k
             if ii % 20 == 0:
-                print("Epoch: {}/{}...".format(e + 1, epochs),
-                      "Training loss: {:.20f}".format(c), "RMS: {:.20f}".format(r), lr_e)
+                say("Epoch: {}/{}...".format(e + 1, epochs),
+                    "Training loss: {:.20f}".format(c), "RMS: {:.20f}".format(r), lr_e)
 
     for e in range(epochs):
         if nepoch_keep_missing > 0:
@@ -315,14 +354,30 @@ def reconstruct(lon, lat, mask, meandata,
         trainer.set_lr(lr_e)
         for ii in range(steps_per_epoch):
             fi, ci, seq = sampler.next_batch()
+            if world > 1:
+                fi, ci, seq = fi[mine], ci[mine], seq[mine]
             trainer.train_step(fi, ci, seq)
         drain(e, 0)
 
         if ((e == epochs - 1) or ((save_each > 0) and (e % save_each == 0))) and outdir is not None:
-            print("Save output", e)
+            say("Save output", e)
             fname = _output_name(outdir)
-            if fast_save:
-                _save_records(recon, fname, lon, lat, meandata, test_len, batch_size)
+            if dist is not None:
+                box = [fname]
+                dist.broadcast_object_list(box, src=0)          # one name (the clock differs by rank)
+                fname = box[0]
+            if fast_save and (dist is None or shard_sweep):
+                if dist is None:
+                    _save_records(recon, fname, lon, lat, meandata, test_len, batch_size)
+                else:
+                    _save_records(recon, fname, lon, lat, meandata, test_len, batch_size, rank, world,
+                                  dist.barrier)
+            elif fast_save:
+                if rank == 0:
+                    _save_records(recon, fname, lon, lat, meandata, test_len, batch_size)
+                dist.barrier()
+            elif rank != 0:
+                dist.barrier()                                   # rank 0 runs the hook path alone
             else:
                 pending = None
                 for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
@@ -335,31 +390,55 @@ def reconstruct(lon, lat, mask, meandata,
                 if pending is not None:
                     _emit(savesample, fname, pending, meandata, lon, lat, e, transfun)
                 _close_writer(fname)
+                if dist is not None:
+                    dist.barrier()
 
-        if (save_model_each > 0) and (e % save_model_each == 0) and outdir is not None:
+        if (save_model_each > 0) and (e % save_model_each == 0) and outdir is not None and rank == 0:
             save_checkpoint(os.path.join(outdir, "model-{:03d}.ckpt".format(e + 1)), trainer)
 
     if writer_tb is not None:
         writer_tb.close()
     dt_end = datetime.now()
-    print(dt_end)
-    print(dt_end - dt_start)
+    say(dt_end)
+    say(dt_end - dt_start)
     return fname
 
 
 _SAVE_SLOTS, _SAVE_THREADS = 6, 3
 
 
-def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size):
+def shard_batches(test_len, batch_size, rank=0, world=1):
+    """Batch numbers [b0, b1) of the reconstruction sweep that ``rank`` takes: contiguous time
+    ranges, whole batches, no overlap (no collective on this path)."""
+    nb = ceil(test_len / batch_size)
+    per = ceil(nb / world)
+    return min(nb, rank * per), min(nb, (rank + 1) * per)
+
+
+def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size, rank=0, world=1,
+                  barrier=None):
     """Reconstruction sweep of the stock output path (:671-689): the device emits the file's
     records batch by batch into a ring of pinned buffers; writer threads wait for a batch's
     copy event and put it into the file with one positional write.  The file is complete and
-    closed on return."""
-    import torch
+    closed on return.
+
+    ``world > 1`` (one process per GPU): every rank reconstructs its own contiguous time range
+    and writes it into the SAME file at the records' own offsets -- rank 0 lays down the header
+    and the fixed variables first and patches the record count last; ``barrier()`` separates
+    the three phases.  No data moves between ranks."""
     from concurrent.futures import ThreadPoolExecutor
-    from .sampler import sequential_batches
-    writer = ncio.ReconWriter(fname, lon, lat, meandata, expect_records=test_len)
+    sharded = world > 1
+    if sharded and barrier is None:
+        raise ValueError("a sharded sweep needs a barrier")
+    writer = None
+    if rank == 0:
+        writer = ncio.ReconWriter(fname, lon, lat, meandata, expect_records=test_len)
+    if sharded:
+        barrier()                                      # the header exists
+        if rank != 0:
+            writer = ncio.ReconWriter(fname, lon, lat, meandata, append=True)
     nslots = len(recon.out_host)
+    b0, b1 = shard_batches(test_len, batch_size, rank, world)
 
     def put(ev, buf, offset, n):
         ev.synchronize()
@@ -368,19 +447,26 @@ def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size):
     futures = [None] * nslots
     try:
         with ThreadPoolExecutor(max_workers=_SAVE_THREADS) as pool:
-            for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
-                slot = ii % nslots
+            for k, ii in enumerate(range(b0, b1)):
+                frames = np.arange(ii * batch_size, min(test_len, (ii + 1) * batch_size), dtype=np.int32)
+                slot = k % nslots
                 if futures[slot] is not None:
                     futures[slot].result()             # the slot's previous batch is in the file
                 out = recon.run_batch(frames, slot=slot)
-                ev = torch.cuda.Event()
-                ev.record()
-                futures[slot] = pool.submit(put, ev, out, ii * batch_size, len(frames))
+                futures[slot] = pool.submit(put, recon.record_event(), out, ii * batch_size, len(frames))
             for f in futures:
                 if f is not None:
                     f.result()
     finally:
-        writer.close()
+        if sharded:
+            if rank != 0:
+                writer.close(finalize=False)
+            barrier()                                  # every rank's records are in the file
+            if rank == 0:
+                writer.numrecs = test_len
+                writer.close()
+        else:
+            writer.close()
 
 
 def _emit(savesample_fn, fname, pending, meandata, lon, lat, e, transfun):

@@ -253,10 +253,13 @@ class RecordFileWriter:
         rec[:, :, self.mask] = self.fill
         self.write_records(offset, rec.reshape(-1).view(np.uint8), n)
 
-    def close(self):
+    def close(self, finalize=True):
+        """``finalize=False``: just drop the descriptor -- for the ranks of a sharded sweep that
+        wrote their record ranges into a file whose header another rank owns."""
         if self.fd is not None:
-            os.pwrite(self.fd, struct.pack(">i", self.numrecs), 4)
-            os.ftruncate(self.fd, self.rec_start + self.numrecs * self.recsize)
+            if finalize:
+                os.pwrite(self.fd, struct.pack(">i", self.numrecs), 4)
+                os.ftruncate(self.fd, self.rec_start + self.numrecs * self.recsize)
             os.close(self.fd)
             self.fd = None
 

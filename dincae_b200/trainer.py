@@ -219,6 +219,12 @@ class Reconstructor:
         self._graphs = {}
         self._seq = 0
 
+    def record_event(self):
+        """Event after everything enqueued so far (the D2H copy of the last ``run_batch``)."""
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
     def _enqueue(self, n):
         net, B = self.net, self.B
         net.n_noncloud.zero_()
