@@ -78,3 +78,18 @@ def test_two_ranks_write_one_file(tmp_path):
                               np.ma.masked_array(np.zeros((1, H, W)), np.zeros((1, H, W), bool)))
     assert os.path.getsize(fname) == w.rec_start + T * w.recsize
     w.close()
+
+
+def test_single_process_sweep_same_protocol(tmp_path):
+    """world = 1 (the path `reconstruct` takes on one GPU): same function, no barrier, masked
+    pixels of meandata keep whatever the device wrote (it writes the fill value there)."""
+    fname = str(tmp_path / "single.nc")
+    lon, lat = np.linspace(0, 1, W), np.linspace(2, 3, H)
+    md = np.ma.masked_array(np.ones((1, H, W)), np.zeros((1, H, W), bool))
+    recon = FakeRecon(2)
+    api._save_records(recon, fname, lon, lat, md, T, B)
+    assert recon.batches == [(o, min(B, T - o)) for o in range(0, T, B)]
+    out = ncio.read_recon(fname)
+    want = np.broadcast_to(np.arange(T, dtype="f4")[:, None, None], (T, H, W))
+    assert np.array_equal(np.ma.getdata(out["mean_rec"]), want)
+    assert np.array_equal(np.ma.getdata(out["meandata"]), np.ones((H, W), "f4"))
