@@ -39,6 +39,19 @@ SIGNATURES = {
     "dincae_conv3x3_wgrad_partial": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
                                              c_int, c_int, c_int, c_int, vp, c_size_t, POINTER(c_int), vp]),
     "dincae_conv3x3_wgrad_reduce": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_conv_weights_bf16_elems": (c_size_t, [c_int, c_int, c_int, POINTER(c_size_t)]),
+    "dincae_conv_weights_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_p4_to_p8": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
+    "dincae_p8_to_p4": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
+    "dincae_conv3x3_fwd_bf16": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int,
+                                        c_int, c_float, vp, vp, vp, vp, c_int, vp]),
+    "dincae_conv3x3_dgrad_bf16": (c_int, [vp, vp, vp, c_float, c_int, vp, c_int, c_int, c_int, c_int,
+                                          c_int, vp, c_float, vp, c_int, vp, vp, vp]),
+    "dincae_conv3x3_wgrad_bf16_workspace": (c_size_t, [c_int, c_int]),
+    "dincae_conv3x3_wgrad_bf16": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, vp, c_float, c_int,
+                                          c_int, c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]),
+    "dincae_head_loss_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_float, vp, vp, vp, vp, vp,
+                                      c_size_t, vp]),
     "dincae_dense_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_dense_fwd": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),

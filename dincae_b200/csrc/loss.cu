@@ -1,7 +1,7 @@
 // Output head and masked Gaussian negative log-likelihood with its backward
 // (DINCAE/__init__.py:520-570): one pass over xrec / xtrue, warp-shuffle + shared-memory
 // reduction, fixed-order final sum by the last block (deterministic).
-#include "common.cuh"
+#include "bf16.cuh"
 
 namespace dincae {
 
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     const float4* __restrict__ xrec, const float2* __restrict__ xtrue, size_t n,
     int truth_uncertain, float neg_slope, const int32_t* __restrict__ n_noncloud,
     float4* __restrict__ g_out, double* __restrict__ sums, float* __restrict__ loss_out,
-    LossWork* __restrict__ work, int round_tf32) {
+    LossWork* __restrict__ work, int gfmt) {
   pdl_trigger();
   pdl_wait();
   const bool normalise = n_noncloud != nullptr;
@@ -108,7 +108,11 @@ __global__ void __launch_bounds__(256) head_loss_kernel(
     }
     ga *= inv_n * (r.x > 0.f ? 1.0f : neg_slope);
     gb *= inv_n * (r.y > 0.f ? 1.0f : neg_slope);
-    g_out[i] = round_tf32 ? make_float4(to_tf32(ga), to_tf32(gb), 0.f, 0.f) : make_float4(ga, gb, 0.f, 0.f);
+    // gfmt 0: fp32, 1: fp32 rounded to TF32, 2: planar-8 bf16 (8 channels in the same 16 bytes)
+    if (gfmt == 2)
+      reinterpret_cast<uint4*>(g_out)[i] = make_uint4(bf2_pack(ga, gb), 0u, 0u, 0u);
+    else
+      g_out[i] = gfmt == 1 ? make_float4(to_tf32(ga), to_tf32(gb), 0.f, 0.f) : make_float4(ga, gb, 0.f, 0.f);
   }
   __shared__ double red[8][4];
   double v[4] = {(double)s_log, (double)s_sq, (double)s_d2, (double)s_w};
@@ -191,10 +195,10 @@ extern "C" size_t dincae_head_loss_workspace(int B, int H, int W) {
   return align_up(16 + (size_t)loss_blocks(n) * 4 * sizeof(double), 256);
 }
 
-extern "C" int dincae_head_loss(const float* xrec, const float* xtrue, int B, int H, int W,
-                                int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
-                                float* g_out, double* sums, float* loss_out, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+static int head_loss_launch(const float* xrec, const float* xtrue, int B, int H, int W,
+                            int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
+                            float* g_out, double* sums, float* loss_out, void* workspace,
+                            size_t workspace_bytes, void* stream, int gfmt) {
   if (!xrec || !xtrue || !g_out || !sums || !loss_out || !workspace || B <= 0 ||
       H <= 0 || W <= 0)
     return DINCAE_EINVAL;
@@ -206,6 +210,22 @@ extern "C" int dincae_head_loss(const float* xrec, const float* xtrue, int B, in
   launch_k(head_loss_kernel, loss_blocks(n), 256, 0, st, 
       reinterpret_cast<const float4*>(xrec), reinterpret_cast<const float2*>(xtrue), n,
       truth_uncertain, neg_slope, n_noncloud, reinterpret_cast<float4*>(g_out), sums, loss_out,
-      reinterpret_cast<LossWork*>(workspace), g_conv_backend == 1);
+      reinterpret_cast<LossWork*>(workspace), gfmt);
   return check_launch();
+}
+
+extern "C" int dincae_head_loss(const float* xrec, const float* xtrue, int B, int H, int W,
+                                int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
+                                float* g_out, double* sums, float* loss_out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  return head_loss_launch(xrec, xtrue, B, H, W, truth_uncertain, neg_slope, n_noncloud, g_out, sums, loss_out,
+                          workspace, workspace_bytes, stream, g_conv_backend == 1 ? 1 : 0);
+}
+
+extern "C" int dincae_head_loss_bf16(const float* xrec, const float* xtrue, int B, int H, int W,
+                                     int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
+                                     void* g_out, double* sums, float* loss_out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return head_loss_launch(xrec, xtrue, B, H, W, truth_uncertain, neg_slope, n_noncloud,
+                          reinterpret_cast<float*>(g_out), sums, loss_out, workspace, workspace_bytes, stream, 2);
 }

@@ -34,34 +34,69 @@ def p4_to_nhwc(x, C):
     return out
 
 
-def cin_map(splits):
+def cin_map(splits, lanes=4):
     """Packed channel index of every TF input channel for a concatenation of sources with
-    ``splits`` channels each (each source padded to whole planes separately)."""
+    ``splits`` channels each (each source padded separately to a multiple of ``lanes``
+    channels: 4 = planar-4 fp32, 8 = planar-8 bf16).  Second value: planes of 4 channels."""
     idx = []
     base = 0
     for c in splits:
         idx.extend(range(base, base + c))
-        base += 4 * planes(c)
+        base += round_up(c, lanes)
     return np.array(idx, dtype=np.int64), base // 4
 
 
-def pack_conv(k_hwio, splits, cout_pad):
+def pack_conv(k_hwio, splits, cout_pad, lanes=4):
     """HWIO [3,3,Cin,Cout] -> WP [9][CinP][cout_pad][4]."""
     kh, kw, cin, cout = k_hwio.shape
     assert (kh, kw) == (3, 3) and sum(splits) == cin and cout <= cout_pad
-    idx, cinp = cin_map(splits)
+    idx, cinp = cin_map(splits, lanes)
     wp = np.zeros((9, cinp, cout_pad, 4), dtype=np.float32)
     k = np.asarray(k_hwio, dtype=np.float32).reshape(9, cin, cout)
     wp[:, idx // 4, :cout, idx % 4] = np.transpose(k, (1, 0, 2))  # advanced idx -> [cin,9,cout]
     return wp
 
 
-def unpack_conv(wp, splits, cout):
+def unpack_conv(wp, splits, cout, lanes=4):
     """WP -> HWIO [3,3,Cin,Cout]."""
-    idx, cinp = cin_map(splits)
+    idx, cinp = cin_map(splits, lanes)
     assert wp.shape[0] == 9 and wp.shape[1] == cinp
     k = wp[:, idx // 4, :cout, idx % 4]           # [cin, 9, cout]
     return np.ascontiguousarray(np.transpose(k, (1, 0, 2))).reshape(3, 3, len(idx), cout)
+
+
+def planes8(c):
+    return (c + 7) // 8
+
+
+def nhwc_to_p8(x):
+    """numpy [B,H,W,C] -> [B,CP8,H,W,8] (zero-padded lanes; cast to bf16 by the caller)."""
+    B, H, W, C = x.shape
+    cp = planes8(C)
+    out = np.zeros((B, cp, H, W, 8), dtype=x.dtype)
+    for c in range(C):
+        out[:, c // 8, :, :, c % 8] = x[..., c]
+    return out
+
+
+def p8_to_nhwc(x, C):
+    """numpy [B,CP8,H,W,8] -> [B,H,W,C]."""
+    B, cp, H, W, _ = x.shape
+    out = np.empty((B, H, W, C), dtype=x.dtype)
+    for c in range(C):
+        out[..., c] = x[:, c // 8, :, :, c % 8]
+    return out
+
+
+def sign_mask8(z_nhwc):
+    """Sign mask of the bf16 path: uint8 [B,CP8,H,4*ceil(W/4)], bit j = lane j of the plane > 0."""
+    B, H, W, C = z_nhwc.shape
+    cp, wq = planes8(C), (W + 3) // 4
+    out = np.zeros((B, cp, H, 4 * wq), dtype=np.uint8)
+    pos = z_nhwc > 0
+    for c in range(C):
+        out[:, c // 8, :, :W] |= (pos[..., c].astype(np.uint8) << np.uint8(c % 8))
+    return out
 
 
 def flat_map(H, W, C):

@@ -155,6 +155,54 @@ int dincae_conv3x3_wgrad(const float* src0, int c0p, int src0_half,
                          float* dw, float* db, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- bf16 convolution path (BASELINE configs[3]: 512x512, bf16 training) --------------------
+ * Activations "planar-8" (P8): bf16 [B][CP8][H][W][8], CP8 = ceil(C/8) planes of 8 channels (16
+ * bytes per pixel and plane, lanes past C zero).  Sign masks: uint8 [B][CP8][H][4*ceil(W/4)], bit j
+ * of the byte of pixel x = lane j of the pre-activation was > 0.  Parameters stay fp32 masters in
+ * the WP layout with every concatenated source padded to a multiple of 8 channels (an even number
+ * of P4 planes); dincae_conv_weights_bf16 converts one layer's kernel into the two bf16 operand
+ * copies the tensor-core kernels read (call it once per optimisation step):
+ *   wf [ceil(cin8/2)][9][2][cout_pad][8]  forward (K = input channels), cout_pad % 16 == 0
+ *   wd [ceil(co8/2)][9][2][nd][8]         data gradient (K = output channels, taps flipped) for
+ *                                         the nd (a multiple of 16, <= 256) input channels from
+ *                                         ci_first on; a layer with more input channels than one
+ *                                         MMA is wide takes one wd and one conv3x3_dgrad_bf16
+ *                                         call per channel range (e.g. c_lo and c_hi separately)
+ * Either of wf / wd may be NULL (that copy is skipped).
+ * dincae_conv_weights_bf16_elems returns the bf16 element count of wf (and of wd through
+ * wd_elems).  All three convolution entry points mirror their fp32 counterparts above (same
+ * fusions, same reference lines DINCAE/__init__.py:442-452, 496-513), with plane counts in units
+ * of 8 channels; they run tcgen05.mma kind::f16 (bf16 operands, fp32 accumulation in TMEM).
+ * conv3x3_fwd_bf16 can additionally write a planar-4 fp32 copy of the activated full-resolution
+ * output (out_f32, out_f32_planes P4 planes): the last decoder layer hands the head / loss kernels
+ * fp32 values.  conv3x3_wgrad_bf16 writes fp32 gradients in the WP layout (cinp4 = 2 * (c0p+c1p)). */
+size_t dincae_conv_weights_bf16_elems(int cinp4, int cout_pad, int nd, size_t* wd_elems);
+int dincae_conv_weights_bf16(const float* wpack, int cinp4, int cout_pad, int ci_first, int nd,
+                             void* wf, void* wd, void* stream);
+int dincae_p4_to_p8(const float* src, int c4, int c8, int B, int H, int W, void* dst, void* stream);
+int dincae_p8_to_p4(const void* src, int c4, int c8, int B, int H, int W, float* dst, void* stream);
+int dincae_conv3x3_fwd_bf16(const void* src0, int c0p, int src0_half, const void* src1, int c1p,
+                            const void* wf, const float* bias, int cout_pad,
+                            int B, int H, int W, int coutp, float neg_slope,
+                            void* out_full, void* out_pool, uint8_t* out_sign,
+                            float* out_f32, int out_f32_planes, void* stream);
+int dincae_conv3x3_dgrad_bf16(const void* g_full, const void* g_pool, const uint8_t* sign,
+                              float neg_slope, int gp, const void* wd, int nd,
+                              int B, int H, int W,
+                              int c_lo, const void* prev_act, float prev_slope, void* g_prev,
+                              int c_hi, void* dx_hi, const void* dx_add, void* stream);
+size_t dincae_conv3x3_wgrad_bf16_workspace(int cinp4, int cout_pad);
+int dincae_conv3x3_wgrad_bf16(const void* src0, int c0p, int src0_half, const void* src1, int c1p,
+                              const void* g_full, const void* g_pool, const uint8_t* sign,
+                              float neg_slope, int gp, int cinp4, int cout_pad,
+                              int B, int H, int W, float* dw, float* db,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* dincae_head_loss with the gradient written as planar-8 bf16 (lanes 0,1; the other 6 zero). */
+int dincae_head_loss_bf16(const float* xrec, const float* xtrue, int B, int H, int W,
+                          int truth_uncertain, float neg_slope, const int32_t* n_noncloud,
+                          void* g_out, double* sums, float* loss_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- dense bottleneck -------------------------------------------------------------- */
 
 /* tf.layers.dense(activation=relu), DINCAE/__init__.py:479-483 (dropout is inert there).
