@@ -19,7 +19,13 @@ class Plan:
     """Static shapes of the network for one (H, W, nvar, filters) configuration."""
 
     def __init__(self, H, W, nvar=10, enc_nfilter_internal=(16, 24, 36, 54),
-                 frac_dense_layer=(0.2,), skipconnections=(1, 2, 3, 4)):
+                 frac_dense_layer=(0.2,), skipconnections=(1, 2, 3, 4), lanes=4):
+        """``lanes`` = 4: planar-4 fp32 activations (TF32 / fp32 kernels); 8: planar-8 bf16
+        activations (kind::f16 kernels; every tensor padded to a multiple of 8 channels, so all
+        plane counts in units of 4 channels are even)."""
+        if lanes not in (4, 8):
+            raise ValueError("lanes must be 4 (fp32 / TF32) or 8 (bf16)")
+        self.lanes = int(lanes)
         self.H, self.W, self.nvar = int(H), int(W), int(nvar)
         self.enc_c = [self.nvar] + [int(c) for c in enc_nfilter_internal]
         self.L = len(self.enc_c) - 1
@@ -30,11 +36,13 @@ class Plan:
         for _ in range(self.L):
             h, w = self.sizes[-1]
             self.sizes.append(((h + 1) // 2, (w + 1) // 2))
-        self.ep = [layout.planes(c) for c in self.enc_c]
-        self.dp = [layout.planes(c) for c in self.dec_c]
+        self.ep = [self._planes(c) for c in self.enc_c]
+        self.dp = [self._planes(c) for c in self.dec_c]
+        self.ep8 = [layout.planes8(c) for c in self.enc_c]
+        self.dp8 = [layout.planes8(c) for c in self.dec_c]
         hL, wL = self.sizes[self.L]
         self.n_bottleneck = hL * wL * self.enc_c[self.L]
-        self.flat_map, self.n_flat = layout.flat_map(hL, wL, self.enc_c[self.L])
+        self.flat_map, self.n_flat = layout.flat_map(hL, wL, self.enc_c[self.L], self.ep[self.L])
         if self.frac:
             fr = self.frac + self.frac[:-1][::-1]
             self.dense_units = [math.floor(self.n_bottleneck * f) for f in fr] + [self.n_bottleneck]
@@ -46,6 +54,10 @@ class Plan:
             last = i == len(self.dense_units) - 1
             self.dense_pad.append(self.n_flat if last else layout.round_up(u, 4))
         self._build_params()
+
+    def _planes(self, c):
+        """Planes of 4 channels a tensor of c channels occupies in this plan's layouts."""
+        return layout.planes(c) if self.lanes == 4 else 2 * layout.planes8(c)
 
     # decoder conv l (1..L): sources and sizes -------------------------------------------
     def dec_sources(self, l):
@@ -59,7 +71,7 @@ class Plan:
         ent = []
 
         def conv(name, splits, cout):
-            cinp = sum(layout.planes(c) for c in splits)
+            cinp = sum(self._planes(c) for c in splits)
             cpad = layout.round_up(cout, COUT_ALIGN)
             ent.append(dict(name=name + "/kernel", kind="conv_w", tf_shape=(3, 3, sum(splits), cout),
                             splits=list(splits), cout=cout, cout_pad=cpad, cinp=cinp,
@@ -128,7 +140,7 @@ class Plan:
             assert tuple(p.shape) == tuple(e["tf_shape"]), (e["name"], p.shape, e["tf_shape"])
             o, n = e["offset"], e["size"]
             if e["kind"] == "conv_w":
-                flat[o:o + n] = layout.pack_conv(p, e["splits"], e["cout_pad"]).reshape(-1)
+                flat[o:o + n] = layout.pack_conv(p, e["splits"], e["cout_pad"], self.lanes).reshape(-1)
             elif e["kind"] == "conv_b":
                 flat[o:o + e["cout"]] = p
             elif e["kind"] == "dense_w":
@@ -147,7 +159,7 @@ class Plan:
             o, n = e["offset"], e["size"]
             if e["kind"] == "conv_w":
                 wp = flat[o:o + n].reshape(9, e["cinp"], e["cout_pad"], 4)
-                out.append(layout.unpack_conv(wp, e["splits"], e["cout"]))
+                out.append(layout.unpack_conv(wp, e["splits"], e["cout"], self.lanes))
             elif e["kind"] == "conv_b":
                 out.append(flat[o:o + e["cout"]].copy())
             elif e["kind"] == "dense_w":
@@ -472,3 +484,312 @@ class Network:
             beta1, beta2, eps, grad_scale, ptr(denom), ptr(self.adam_state),
             ptr(self.workspace), self.workspace.numel(), stream_ptr()),
             28 * self.plan.n_params_tf, 0)
+
+
+def make_network(plan, max_batch, train=True, device=None):
+    """Network for ``plan``: planar-4 fp32 / TF32 kernels, or (``plan.lanes == 8``) the bf16 path."""
+    cls = NetworkBF16 if plan.lanes == 8 else Network
+    return cls(plan, max_batch, train=train, device=device)
+
+
+class NetworkBF16(Network):
+    """bf16 execution of the same graph (BASELINE configs[3]: "bf16 training"): activations and
+    their gradients are planar-8 bf16, the convolutions run ``tcgen05.mma kind::f16`` with fp32
+    accumulation (``csrc/conv_bf16.cu``, ``csrc/conv_wgrad_bf16.cu``), parameters, gradients of
+    the parameters, Adam state, the dense bottleneck, the network output and the loss stay fp32.
+    The fp32 master kernels are converted to their bf16 operand copies once per step."""
+
+    def __init__(self, plan, max_batch, train=True, device=None):
+        import os
+        if plan.lanes != 8:
+            raise ValueError("NetworkBF16 needs Plan(lanes=8)")
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DincaeError("dincae_b200 needs a CUDA device (no CPU fallback)")
+        self.plan = plan
+        self.Bmax = int(max_batch)
+        self.train = train
+        self.dev = torch.device(device if device is not None else "cuda")
+        P, B, dev = plan, self.Bmax, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        L = P.L
+
+        self.params = torch.zeros(P.n_params_flat, **f32)
+        if train:
+            self.grads = torch.zeros(P.n_params_flat, **f32)
+            self.adam_m = torch.zeros(P.n_params_flat, **f32)
+            self.adam_v = torch.zeros(P.n_params_flat, **f32)
+            self.adam_state = torch.zeros(8, **f32)
+            self.lr = torch.zeros(1, **f32)
+            self.reset_optimizer()
+
+        # the batch builder writes planar-4 fp32 with exactly ceil(nvar/4) planes
+        self.x0_planes = layout.planes(P.nvar)
+        self.X = [torch.zeros(B, self.x0_planes, P.H, P.W, 4, **f32)]
+        self.X8 = [torch.zeros(B, P.ep8[k], P.sizes[k][0], P.sizes[k][1], 8, **b16) for k in range(L + 1)]
+        self.xtrue = torch.zeros(B, P.H, P.W, 2, **f32)
+        self.n_noncloud = torch.zeros(1, dtype=torch.int32, device=dev)
+        nd = len(P.dense_units)
+        hL, wL = P.sizes[L]
+        self.F = [torch.zeros(B, P.n_flat, **f32)] if nd else []
+        for i in range(nd):
+            self.F.append(torch.zeros(B, P.dense_pad[i + 1], **f32))
+        self.D8 = [torch.zeros(B, P.ep8[L], hL, wL, 8, **b16) if nd else self.X8[L]]
+        for l in range(1, L):
+            h, w = P.sizes[L - l]
+            self.D8.append(torch.zeros(B, P.dp8[l], h, w, 8, **b16))
+        self.D8.append(None)                                    # the last layer only writes xrec
+        self.xrec = torch.zeros(B, 1, P.H, P.W, 4, **f32)
+        self.D = [None] * L + [self.xrec]                       # head kernels read D[L]
+        self.m_rec = torch.zeros(B, P.H, P.W, **f32)
+        self.s2_rec = torch.zeros(B, P.H, P.W, **f32)
+
+        # bf16 operand copies of the conv kernels: forward copy per layer, data-gradient copies
+        # per channel range of at most 256 input channels
+        self._wbf = {}
+        total = 0
+        import ctypes
+        for e in P.entries:
+            if e["kind"] != "conv_w":
+                continue
+            name = e["name"][:-7]
+            nde = ctypes.c_size_t(0)
+            nf = self.lib.dincae_conv_weights_bf16_elems(e["cinp"], e["cout_pad"], 16, ctypes.byref(nde))
+            info = dict(wf=(total, nf), wd=[])
+            total += layout.round_up(nf, 64)
+            if train:
+                for (ci_first, lo, hi) in self._dgrad_ranges(name):
+                    ndr = layout.round_up(8 * (lo + hi), 16)
+                    self.lib.dincae_conv_weights_bf16_elems(e["cinp"], e["cout_pad"], ndr, ctypes.byref(nde))
+                    info["wd"].append(dict(ci_first=ci_first, lo=lo, hi=hi, nd=ndr, off=total, n=nde.value))
+                    total += layout.round_up(nde.value, 64)
+            self._wbf[name] = info
+        self.wbf = torch.zeros(total, **b16)
+
+        ws = [self.lib.dincae_dense_workspace(B, P.dense_pad[i], P.dense_pad[i + 1]) for i in range(nd)]
+        if train:
+            self.S8 = [None] + [
+                torch.zeros(B, P.ep8[l], P.sizes[l - 1][0], 4 * ((P.sizes[l - 1][1] + 3) // 4),
+                            dtype=torch.uint8, device=dev) for l in range(1, L + 1)]
+            self.GD8 = [torch.zeros_like(self.D8[l]) if (l > 0 or nd) else None for l in range(L)]
+            self.GD8.append(torch.zeros(B, 1, P.H, P.W, 8, **b16))
+            self.dX8 = [None] + [torch.zeros_like(self.X8[k]) for k in range(1, L + 1)]
+            if not nd:
+                self.GD8[0] = self.dX8[L]                       # decoder 1 back-propagates straight into the encoder
+            self.dXskip8 = [None] * (L + 1)
+            for l in range(1, L + 1):
+                _, sk, r = P.dec_sources(l)
+                if sk and r >= 1:
+                    self.dXskip8[r] = torch.zeros_like(self.X8[r])
+            self.dZ = [None] + [torch.zeros_like(self.F[i + 1]) for i in range(nd)]
+            self.dF0 = torch.zeros(B, P.n_flat, **f32) if nd else None
+            self.loss_sums = torch.zeros(4, dtype=torch.float64, device=dev)
+            self.loss_out = torch.zeros(2, **f32)
+            self.l2_out = torch.zeros(1, **f32)
+            ws.append(self.lib.dincae_head_loss_workspace(B, P.H, P.W))
+            ws.append(self.lib.dincae_adam_workspace(P.n_params_flat))
+            for e in P.entries:
+                if e["kind"] == "conv_w":
+                    ws.append(self.lib.dincae_conv3x3_wgrad_bf16_workspace(e["cinp"], e["cout_pad"]))
+        self.workspace = torch.zeros(max(ws + [256]), dtype=torch.uint8, device=dev)
+        self._side_parts = int(os.environ.get("DINCAE_SIDE_PARTS", "7"))
+        self.side = torch.cuda.Stream(device=dev) if (train and os.environ.get("DINCAE_NO_SIDE_STREAM") != "1") else None
+        self.workspace_side = torch.zeros_like(self.workspace) if train else None
+        self._ent = {e["name"]: e for e in P.entries}
+        self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
+        self.tracer = None
+
+    # ---- bf16 operand copies of the kernels -----------------------------------------------------
+    def _dgrad_ranges(self, name):
+        """[(first input channel, planes of the half-res source, planes of the skip source)]: the
+        channel ranges (at most 256 channels = one MMA each) whose data gradient layer ``name``
+        computes."""
+        P = self.plan
+        names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
+        idx = names.index(name)
+        if idx < P.L:                                   # encoder layer idx+1: gradient of its input
+            return [(0, 0, P.ep8[idx])] if idx >= 1 else []
+        l = idx - P.L + 1
+        up, sk, r = P.dec_sources(l)
+        lo = P.dp8[l - 1] if l > 1 else P.ep8[P.L]
+        hi = P.ep8[r] if (sk and r >= 1) else 0
+        if 8 * (lo + hi) <= 256:
+            return [(0, lo, hi)]
+        return [(0, lo, 0)] + ([(8 * lo, 0, hi)] if hi else [])
+
+    def _wf(self, name):
+        off, n = self._wbf[name]["wf"]
+        return self.wbf[off: off + n]
+
+    def prepare_weights(self):
+        """fp32 master kernels -> bf16 operand copies (one small launch per layer and copy)."""
+        st = stream_ptr()
+        for name, info in self._wbf.items():
+            e = self._ent[name + "/kernel"]
+            w = self._w(e["name"])
+            wds = info["wd"]
+            first = wds[0] if wds else None
+            self._call("conv_weights_bf16(%s)" % name, "dincae_conv_weights_bf16", (
+                ptr(w), e["cinp"], e["cout_pad"], first["ci_first"] if first else 0,
+                first["nd"] if first else 16, ptr(self._wf(name)),
+                ptr(self.wbf[first["off"]:]) if first else None, st), 6 * e["size"], 0)
+            for d in wds[1:]:
+                self._call("conv_weights_bf16(%s)" % name, "dincae_conv_weights_bf16", (
+                    ptr(w), e["cinp"], e["cout_pad"], d["ci_first"], d["nd"], None,
+                    ptr(self.wbf[d["off"]:]), st), 6 * e["size"], 0)
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def forward(self, B, save_signs=None):
+        P, st = self.plan, stream_ptr()
+        L = P.L
+        save_signs = self.train if save_signs is None else save_signs
+        self.prepare_weights()
+        h0, w0 = P.sizes[0]
+        self._call("p4_to_p8(input)", "dincae_p4_to_p8", (
+            ptr(self.X[0]), self.x0_planes, P.ep8[0], B, h0, w0, ptr(self.X8[0]), st),
+            6 * B * h0 * w0 * P.nvar, 0)
+        for l in range(1, L + 1):
+            h, w = P.sizes[l - 1]
+            name = self._enc_name(l)
+            e = self._ent[name + "/kernel"]
+            ci, co = P.enc_c[l - 1], P.enc_c[l]
+            hh, wh = P.sizes[l]
+            nb = 2 * B * (h * w * ci + hh * wh * co) + 18 * ci * co + (B * h * w * co // 8 if save_signs else 0)
+            self._call("conv3x3_fwd(enc %d)" % l, "dincae_conv3x3_fwd_bf16", (
+                ptr(self.X8[l - 1]), P.ep8[l - 1], 0, None, 0,
+                ptr(self._wf(name)), ptr(self._w(name + "/bias")), e["cout_pad"],
+                B, h, w, P.ep8[l], NEG_SLOPE, None, ptr(self.X8[l]),
+                ptr(self.S8[l]) if save_signs else None, None, 0, st), nb, 18 * ci * co * B * h * w)
+        nd = len(P.dense_units)
+        hL, wL = P.sizes[L]
+        if nd:
+            self._call("p8_to_p4(bottleneck)", "dincae_p8_to_p4", (
+                ptr(self.X8[L]), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.F[0]), st),
+                6 * B * P.n_bottleneck, 0)
+        for i in range(nd):
+            name = "dense" if i == 0 else "dense_%d" % i
+            kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._call("dense_fwd(%d)" % i, "dincae_dense_fwd", (
+                ptr(self.F[i]), ptr(self._w(name + "/kernel")), ptr(self._w(name + "/bias")),
+                B, P.dense_pad[i], P.dense_pad[i + 1], 1, ptr(self.F[i + 1]),
+                ptr(self.workspace), self.workspace.numel(), st),
+                4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
+        if nd:
+            self._call("p4_to_p8(bottleneck)", "dincae_p4_to_p8", (
+                ptr(self.F[nd]), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.D8[0]), st),
+                6 * B * P.n_bottleneck, 0)
+        for l in range(1, L + 1):
+            up, sk, r = P.dec_sources(l)
+            h, w = P.sizes[r]
+            name = self._dec_name(l)
+            e = self._ent[name + "/kernel"]
+            hh, wh = P.sizes[r + 1]
+            co = P.dec_c[l]
+            last = l == L
+            nb = 2 * B * (hh * wh * up + h * w * sk) + (4 if last else 2) * B * h * w * co + 18 * (up + sk) * co
+            c0p8 = P.dp8[l - 1] if l > 1 else P.ep8[L]
+            self._call("conv3x3_fwd(dec %d)" % l, "dincae_conv3x3_fwd_bf16", (
+                ptr(self.D8[l - 1]), c0p8, 1,
+                ptr(self.X8[r]) if sk else None, P.ep8[r] if sk else 0,
+                ptr(self._wf(name)), ptr(self._w(name + "/bias")), e["cout_pad"],
+                B, h, w, P.dp8[l], NEG_SLOPE, None if last else ptr(self.D8[l]), None, None,
+                ptr(self.xrec) if last else None, 1 if last else 0, st),
+                nb, 18 * (up + sk) * co * B * h * w)
+
+    # ---- loss + backward ------------------------------------------------------------------------------
+    def loss_backward(self, B, truth_uncertain=False, normalise=True, phase=0):
+        if phase == 0:
+            self.loss_backward(B, truth_uncertain, normalise, 1)
+            self.loss_backward(B, truth_uncertain, normalise, 2)
+            return
+        P, st = self.plan, stream_ptr()
+        L = P.L
+        wsp, wsn = ptr(self.workspace), self.workspace.numel()
+        wss = ptr(self.workspace_side)
+        nd = len(P.dense_units)
+        if phase == 2:
+            return self._backward_encoder(B, wss, wsn, st)
+        self._call("head_loss", "dincae_head_loss_bf16", (
+            ptr(self.xrec), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
+            ptr(self.n_noncloud) if normalise else None, ptr(self.GD8[L]), ptr(self.loss_sums),
+            ptr(self.loss_out), wsp, wsn, st), 40 * B * P.H * P.W, 0)
+        for l in range(L, 0, -1):
+            up, sk, r = P.dec_sources(l)
+            h, w = P.sizes[r]
+            name = self._dec_name(l)
+            e = self._ent[name + "/kernel"]
+            c0p8 = P.dp8[l - 1] if l > 1 else P.ep8[L]
+            c1p8 = P.ep8[r] if sk else 0
+            hh, wh = P.sizes[r + 1]
+            co = P.dec_c[l]
+            nb = 2 * B * (hh * wh * up + h * w * (sk + co)) + 36 * (up + sk) * co
+            self._fork(lambda: self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad_bf16", (
+                ptr(self.D8[l - 1]), c0p8, 1, ptr(self.X8[r]) if sk else None, c1p8,
+                ptr(self.GD8[l]), None, None, NEG_SLOPE, P.dp8[l], e["cinp"], e["cout_pad"], B, h, w,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                wss, wsn, stream_ptr()), nb, 18 * (up + sk) * co * B * h * w), 1)
+            prev_slope = NEG_SLOPE if l > 1 else (0.0 if nd else 1.0)
+            prev_act = self.D8[l - 1] if (l > 1 or nd) else None
+            want_skip = bool(sk) and r >= 1
+            cin_eff = up + (sk if want_skip else 0)
+            nb = 2 * B * (h * w * co + 2 * hh * wh * up + (h * w * sk if want_skip else 0)) + 18 * cin_eff * co
+            for d in self._wbf[name]["wd"]:
+                lo, hi = d["lo"] > 0, d["hi"] > 0
+                self._call("conv3x3_dgrad(dec %d)" % l, "dincae_conv3x3_dgrad_bf16", (
+                    ptr(self.GD8[l]), None, None, NEG_SLOPE, P.dp8[l], ptr(self.wbf[d["off"]:]), d["nd"],
+                    B, h, w,
+                    c0p8 if lo else 0, ptr(prev_act) if lo else None, prev_slope if lo else 1.0,
+                    ptr(self.GD8[l - 1]) if lo else None,
+                    c1p8 if hi else 0, ptr(self.dXskip8[r]) if hi else None, None, st),
+                    nb, 18 * cin_eff * co * B * h * w)
+        hL, wL = P.sizes[L]
+        if nd:
+            self._call("p8_to_p4(bottleneck grad)", "dincae_p8_to_p4", (
+                ptr(self.GD8[0]), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.dZ[nd]), st),
+                6 * B * P.n_bottleneck, 0)
+        for i in range(nd - 1, -1, -1):
+            name = "dense" if i == 0 else "dense_%d" % i
+            K, N = P.dense_pad[i], P.dense_pad[i + 1]
+            kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._fork(lambda: self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
+                ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                stream_ptr()), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn), 2)
+            dst = self.dZ[i] if i > 0 else self.dF0
+            self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
+                ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
+                ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
+                4 * (B * nn + kk * nn + B * kk), 2 * B * kk * nn)
+        if nd:
+            self._call("p4_to_p8(bottleneck grad)", "dincae_p4_to_p8", (
+                ptr(self.dF0), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.dX8[L]), st),
+                6 * B * P.n_bottleneck, 0)
+        self._join()
+
+    def _backward_encoder(self, B, wss, wsn, st):
+        P, L = self.plan, self.plan.L
+        for l in range(L, 0, -1):
+            h, w = P.sizes[l - 1]
+            name = self._enc_name(l)
+            e = self._ent[name + "/kernel"]
+            gpool = self.dX8[l]
+            ci, co = P.enc_c[l - 1], P.enc_c[l]
+            hh, wh = P.sizes[l]
+            nb = 2 * B * (h * w * ci + hh * wh * co) + B * h * w * co // 8 + 36 * ci * co
+            self._fork(lambda: self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad_bf16", (
+                ptr(self.X8[l - 1]), P.ep8[l - 1], 0, None, 0,
+                None, ptr(gpool), ptr(self.S8[l]), NEG_SLOPE, P.ep8[l], e["cinp"], e["cout_pad"], B, h, w,
+                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                wss, wsn, stream_ptr()), nb, 18 * ci * co * B * h * w), 4)
+            if l > 1:
+                has_add = self.dXskip8[l - 1] is not None
+                d = self._wbf[name]["wd"][0]
+                nb = 2 * B * (hh * wh * co + h * w * ci * (2 if has_add else 1)) + B * h * w * co // 8 + 18 * ci * co
+                self._call("conv3x3_dgrad(enc %d)" % l, "dincae_conv3x3_dgrad_bf16", (
+                    None, ptr(gpool), ptr(self.S8[l]), NEG_SLOPE, P.ep8[l], ptr(self.wbf[d["off"]:]), d["nd"],
+                    B, h, w, 0, None, 1.0, None,
+                    P.ep8[l - 1], ptr(self.dX8[l - 1]),
+                    ptr(self.dXskip8[l - 1]) if has_add else None, st),
+                    nb, 18 * ci * co * B * h * w)
+        self._join()

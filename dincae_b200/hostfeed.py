@@ -13,7 +13,7 @@ from math import ceil
 import numpy as np
 import torch
 
-from .engine import Network
+from .engine import Network, make_network
 
 
 def _repeat(gen_fn):
@@ -46,7 +46,7 @@ def reconstruct_from_generators(plan, lon, lat, mask, meandata, train_datagen, t
                                 regularization_L2_beta, transfun, savesample, learning_rate,
                                 learning_rate_decay_epoch, init_seed, shuffle_seed, loss,
                                 output_name, close_writer):
-    net = Network(plan, batch_size, train=True)
+    net = make_network(plan, batch_size, train=True)
     net.set_params_tf(plan.glorot_init(init_seed))
     rs = np.random.RandomState(shuffle_seed)
     stream = _repeat(train_datagen)

@@ -99,10 +99,12 @@ def sign_mask8(z_nhwc):
     return out
 
 
-def flat_map(H, W, C):
-    """Planar-flatten index of every NHWC-flatten index of an [H,W,C] tensor."""
+def flat_map(H, W, C, cp=None):
+    """Planar-flatten index of every NHWC-flatten index of an [H,W,C] tensor stored with
+    ``cp`` planes of 4 channels (default: ceil(C/4))."""
     y, x, c = np.meshgrid(np.arange(H), np.arange(W), np.arange(C), indexing="ij")
-    return ((((c // 4) * H + y) * W + x) * 4 + c % 4).reshape(-1), planes(C) * H * W * 4
+    cp = planes(C) if cp is None else cp
+    return ((((c // 4) * H + y) * W + x) * 4 + c % 4).reshape(-1), cp * H * W * 4
 
 
 def pack_dense(w, rows_map, rows_n, cols_map, cols_n):

@@ -14,7 +14,7 @@ batch of N*B.
 import numpy as np
 import torch
 
-from .engine import Network
+from .engine import Network, make_network
 
 
 class Trainer:
@@ -28,7 +28,7 @@ class Trainer:
         self.l2_beta = float(l2_beta)
         self.noise_seed = int(noise_seed)
         self.jitter_std = jitter_std
-        self.net = Network(plan, self.B, train=True, device=cube.dev)
+        self.net = make_network(plan, self.B, train=True, device=cube.dev)
         self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
         self.dist = None
         self.rank, self.world = 0, 1
@@ -189,7 +189,7 @@ class Reconstructor:
         ``meandata`` is masked) instead of (m_rec, sigma2_rec) -- the per-batch arithmetic of
         ``savesample`` runs on the device (``dincae_head_recon_records``)."""
         self.plan, self.cube, self.B = plan, cube, int(batch_size)
-        self.net = net if net is not None else Network(plan, self.B, train=False, device=cube.dev)
+        self.net = net if net is not None else make_network(plan, self.B, train=False, device=cube.dev)
         self.train_mode_inputs = train_mode_inputs       # reference quirk Q1
         self.noise_seed = noise_seed
         self.jitter_std = jitter_std

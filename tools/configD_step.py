@@ -8,13 +8,14 @@ from dincae_b200.engine import Plan
 from dincae_b200.sampler import TrainSampler
 from dincae_b200.trainer import Trainer, Reconstructor
 T, H, W, B = 12, 512, 512, int(sys.argv[1]) if len(sys.argv) > 1 else 4
+LANES = 8 if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else 4
 fields, missing = [], []
 for k in range(4):
     lon, lat, time_, data, mask = synthetic.sst_like_cube(T=T, H=H, W=W, seed=100 + k)
     fields.append(data); missing.append(np.ma.getmaskarray(data))
 cube = DeviceCube(lon, lat, time_, fields, missing, [1.0] * 4, 3)
 print("nvar", cube.nvar)
-plan = Plan(H, W, cube.nvar, (32, 48, 72, 108, 162), (0.2,), (1, 2, 3, 4, 5))
+plan = Plan(H, W, cube.nvar, (32, 48, 72, 108, 162), (0.2,), (1, 2, 3, 4, 5), lanes=LANES)
 tr = Trainer(plan, cube, B, noise_seed=1, jitter_std=[0.05] * 4, use_graph=False)
 tr.set_lr(1e-3)
 random.seed(3)
