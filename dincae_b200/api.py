@@ -15,6 +15,28 @@ __all__ = ["reconstruct", "load_gridded_nc", "data_generator", "reconstruct_grid
 
 NEAREST_NEIGHBOR = 1        # tf.image.ResizeMethod.NEAREST_NEIGHBOR in TF 1.15
 
+# Arithmetic of the convolutions (new capability; the reference is fp32 throughout):
+#   "tf32" (default) tcgen05 kind::tf32 on planar-4 fp32 activations,
+#   "bf16"           tcgen05 kind::f16 on planar-8 bf16 activations (BASELINE configs[3]),
+#   "fp32"           FFMA kernels, bit-for-bit fp32.
+# Set with set_precision() or the environment variable DINCAE_PRECISION; the reference's
+# keyword list of `reconstruct` stays unchanged.
+_precision = [None]
+
+
+def set_precision(name):
+    """Select the convolution arithmetic of subsequent `reconstruct*` calls (see above)."""
+    if name not in ("tf32", "bf16", "fp32", None):
+        raise ValueError("precision must be 'tf32', 'bf16' or 'fp32'")
+    _precision[0] = name
+
+
+def get_precision():
+    name = _precision[0] or os.environ.get("DINCAE_PRECISION", "tf32").lower()
+    if name not in ("tf32", "bf16", "fp32"):
+        raise ValueError("DINCAE_PRECISION must be tf32, bf16 or fp32 (got %r)" % name)
+    return name
+
 
 def identity(x):
     return x
@@ -280,7 +302,13 @@ def reconstruct(lon, lat, mask, meandata,
         dist.barrier()
 
     jmax, imax = mask.shape
-    plan = Plan(jmax, imax, nvar, enc_nfilter_internal, frac_dense_layer, skipconnections)
+    precision = get_precision()
+    plan = Plan(jmax, imax, nvar, enc_nfilter_internal, frac_dense_layer, skipconnections,
+                lanes=8 if precision == "bf16" else 4)
+    if precision != "bf16":
+        from . import _lib
+        _lib.check(_lib.load().dincae_set_conv_backend(0 if precision == "fp32" else 1), "set_conv_backend")
+    say("precision ", precision)
 
     if not isinstance(train_datagen, FrameSource) or not isinstance(test_datagen, FrameSource):
         if dist is not None:

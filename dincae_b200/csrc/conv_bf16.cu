@@ -26,7 +26,7 @@ namespace dincae {
 constexpr int BF_LOAD_WARPS = 6;
 constexpr int BF_MMA_WARP = BF_LOAD_WARPS;
 constexpr int BF_EPI_WARP0 = BF_LOAD_WARPS + 1;
-constexpr int BF_EPI_WARPS = 8;
+constexpr int BF_EPI_WARPS = 16;             // four per TMEM lane quadrant: the epilogue is latency-bound
 constexpr int BF_THREADS = 32 * (BF_LOAD_WARPS + 1 + BF_EPI_WARPS);
 constexpr int BF_ROWS = 16;
 constexpr int BF_IN_ROWS = BF_ROWS + 2;
@@ -41,6 +41,7 @@ struct BfPlan {
   int plane_elems;                            // smem plane stride of the A block (16-byte units, 128-byte multiple)
   int a_elems, w_elems, stage_elems;          // 16-byte units
   int tma0, tma1;
+  int tma_only;                               // every input plane arrives by TMA: one loader warp does it all
 };
 
 struct BfConvParams {
@@ -89,7 +90,7 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_holder;
-  __shared__ float bias_s[BF_MAX_N + 8];
+  __shared__ __align__(16) float bias_s[BF_MAX_N + 8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = L.n_stages;
@@ -97,7 +98,7 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
   pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], BF_LOAD_WARPS);
+      mbar_init(&full_bar[s], L.tma_only ? 1 : BF_LOAD_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tfull_bar[0], 1);
@@ -126,6 +127,8 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
 
   if (warp < BF_LOAD_WARPS) {
     // =============================== operand loader ===========================================
+    // (with every plane on the TMA path warps 1.. have nothing to stage and stay out of the way)
+    if (!L.tma_only || warp == 0) {
     const int Kp = P.p0 + P.p1;
     const int sh0 = (SRCM == 1) ? 1 : P.half0;
     const int ps0 = sh0 ? P.Hh * P.Wh : P.H * P.W;          // plane strides (pixels)
@@ -229,6 +232,7 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
         if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
+    }
   } else if (warp == BF_MMA_WARP) {
     // =============================== MMA issuer ===============================================
     const uint32_t idesc = umma_idesc_bf16(128, L.Nmma, 0, 0);
@@ -298,12 +302,15 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
       }
       mbar_wait(&tfull_bar[buf], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
-      for (int j = jh; j < L.Xb; j += BF_EPI_WARPS / 4) {
+      // work units = (M-tile j, pair of output planes), dealt round-robin to the warps of a quadrant
+      const int npair = (P.out_planes + 1) >> 1;
+      for (int unit = jh; unit < L.Xb * npair; unit += BF_EPI_WARPS / 4) {
+        const int j = unit / npair, p0 = 2 * (unit - j * npair);
         const int x = xt + 8 * j;
         const bool valid = row_ok && (x < P.W);
         const float pool_scale = inv_cy * ((x + 1 < P.W) ? 0.5f : 1.0f);
         const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * L.acc_cols + j * L.Nmma);
-        for (int p0 = 0; p0 < P.out_planes; p0 += 2) {
+        {
           float acc[16];
           tmem_ld16(t0 + (uint32_t)(8 * p0), acc);
           if (MODE == 0) {
@@ -311,9 +318,12 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
               unsigned bits = 0;
+              const float4 b0 = reinterpret_cast<const float4*>(bias_s)[2 * (p0 + qq)];
+              const float4 b1 = reinterpret_cast<const float4*>(bias_s)[2 * (p0 + qq) + 1];
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                float a = acc[8 * qq + c] + bias_s[8 * (p0 + qq) + c];
+                float a = acc[8 * qq + c] + bv[c];
                 bits |= (a > 0.f ? 1u : 0u) << c;
                 a = a > 0.f ? a : slope * a;
                 acc[8 * qq + c] = valid ? a : 0.f;
@@ -456,7 +466,7 @@ static bool conv_bf16_plan(int Kp, int out_planes, int B, int H, int W, BfPlan& 
   if (ns > BF_MAX_STAGES) ns = BF_MAX_STAGES;
   if (ns < 2) return false;
   L.n_stages = ns;
-  L.tma0 = L.tma1 = 0;
+  L.tma0 = L.tma1 = L.tma_only = 0;
   L.acc_cols = Xb * L.Nmma;
   L.tmem_cols = bf_pow2_cols(2 * L.acc_cols);
   return true;
@@ -515,6 +525,7 @@ static int launch_conv_bf16(int mode, int srcm, BfConvParams& P, cudaStream_t st
       Q.m.tma1 = 1;
     }
   }
+  Q.m.tma_only = (srcm == 0 && Q.m.tma0 && (P.p1 == 0 || Q.m.tma1)) ? 1 : 0;
   Q.c = P;
   const size_t smem = (size_t)Q.m.n_stages * Q.m.stage_elems * 16 + 128;
   if (!attr_set[which]) {

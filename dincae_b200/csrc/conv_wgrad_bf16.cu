@@ -25,13 +25,14 @@
 #include "umma.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dincae {
 
-constexpr int WB_LOAD_WARPS = 8;
-constexpr int WB_MMA_WARP = WB_LOAD_WARPS;
-constexpr int WB_THREADS = 32 * (WB_LOAD_WARPS + 1);
+constexpr int WB_MAX_LOAD_WARPS = 16;          // loader warps (a multiple of 4) + one MMA warp; runtime choice
+constexpr int WB_THREADS = 32 * (WB_MAX_LOAD_WARPS + 1);
 constexpr int WB_MAX_STAGES = 3;
 constexpr int WB_SMEM_BUDGET = 214 * 1024;
 
@@ -53,15 +54,24 @@ struct WgBfParams {
   int sbo_u, sbo_g, u_bytes, stage_bytes, n_stages;
   int tmem_cols;
   int tma_u0, tma_u1, tma_g;
+  int toff[12];                // per tap: dy * TWu + dx (16-byte units), precomputed on the host
+  unsigned idesc;              // instruction descriptor and the constant halves of the operand descriptors
+  unsigned long long a_hi, b_hi;
+  int load_warps, poll_all;    // experiment knobs (DINCAE_WB_WARPS, DINCAE_WB_POLL_ALL)
+  long long* dbg;              // DINCAE_WB_DEBUG=1: role timeline of CTA 0 ([2][256][4] clock64 values)
 };
 
-// one pixel row of a register-path plane: up to 4 x 32 pixels
-template <int KIND>   // 0: x2-upsampled U plane, 1: un-pooled G plane
-__device__ __forceinline__ void wb_row(const WgBfParams& P, int b, int plane, int y, int x_first, int width,
-                                       uint4* dst, int lane) {
-  const bool yok = (unsigned)y < (unsigned)P.H;
+// One pixel row of a register-path plane (up to 4 x 32 pixels) in two halves, so that the loads of
+// all rows a warp owns in a tile are in flight before the first one is used.
+struct WbRow {
   uint4 v[4];
   unsigned sb[4];
+};
+
+template <int KIND>   // 0: x2-upsampled U plane, 1: un-pooled G plane
+__device__ __forceinline__ void wb_issue(const WgBfParams& P, int b, int plane, int y, int x_first, int width,
+                                         int lane, WbRow& row) {
+  const bool yok = (unsigned)y < (unsigned)P.H;
   const uint4* src;
   const uint8_t* sg = nullptr;
   if (KIND == 0) {
@@ -74,17 +84,22 @@ __device__ __forceinline__ void wb_row(const WgBfParams& P, int b, int plane, in
   for (int u = 0; u < 4; ++u) {
     const int px = lane + 32 * u, x = x_first + px;
     const bool ok = yok && px < width && (unsigned)x < (unsigned)P.W;
-    v[u] = ldg_u4_pred(src + (x >> 1), ok);
-    sb[u] = 0;
-    if (KIND == 1) sb[u] = ldg_u8_pred(sg + x, ok);
+    row.v[u] = ldg_u4_pred(src + (x >> 1), ok);
+    row.sb[u] = 0;
+    if (KIND == 1) row.sb[u] = ldg_u8_pred(sg + x, ok);
   }
+}
+
+template <int KIND>
+__device__ __forceinline__ void wb_commit(const WgBfParams& P, int y, int x_first, int width, uint4* dst, int lane,
+                                          const WbRow& row) {
   const float inv_y = (2 * (y >> 1) + 1 < P.H) ? 0.5f : 1.0f;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int px = lane + 32 * u, x = x_first + px;
     if (px < width) {
-      uint4 t = v[u];
-      if (KIND == 1) t = bf8_unpool(t, sb[u], inv_y * ((2 * (x >> 1) + 1 < P.W) ? 0.5f : 1.0f), P.slope);
+      uint4 t = row.v[u];
+      if (KIND == 1) t = bf8_unpool(t, row.sb[u], inv_y * ((2 * (x >> 1) + 1 < P.W) ? 0.5f : 1.0f), P.slope);
       dst[px] = t;
     }
   }
@@ -101,6 +116,8 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
   __shared__ uint32_t tmem_holder;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int WB_LOAD_WARPS = P.load_warps, WB_MMA_WARP = P.load_warps;
+  const int nthreads = 32 * (P.load_warps + 1);
   const int job = blockIdx.x % P.jobs, split = blockIdx.x / P.jobs;
   const int mt = job % P.mt_count, tg = job / P.mt_count;
   const int tap0 = tg * P.tpg;
@@ -114,7 +131,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
   pdl_trigger();
   {
     const int n16 = (S * P.stage_bytes + (P.slots - P.u_alloc) * P.sbo_u) >> 4;
-    for (int i = tid; i < n16; i += WB_THREADS) reinterpret_cast<uint4*>(ring)[i] = u4_zero();
+    for (int i = tid; i < n16; i += nthreads) reinterpret_cast<uint4*>(ring)[i] = u4_zero();
   }
   __syncthreads();
   if (mt == P.ones_mt) {
@@ -122,7 +139,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
     const int npx = P.sbo_u >> 4;
     for (int s = 0; s < S; ++s) {
       uint4* pl = reinterpret_cast<uint4*>(ring + (size_t)s * P.stage_bytes + (size_t)P.ones_slot * P.sbo_u);
-      for (int i = tid; i < npx; i += WB_THREADS) pl[i] = make_uint4(0x3f80u, 0u, 0u, 0u);
+      for (int i = tid; i < npx; i += nthreads) pl[i] = make_uint4(0x3f80u, 0u, 0u, 0u);
     }
   }
   if (tid == 0) {
@@ -166,13 +183,44 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
     if (P.tma_g) tx_bytes += (uint32_t)(P.gp * P.R * g_row_bytes);
     int s = 0;
     uint32_t ph = 0;
+    int dbg_n = 0;
     for (int tile = split; tile < P.n_tiles; tile += P.splits) {
       const int b = tile / per_img, rem = tile - b * per_img;
       const int rb = rem / P.tiles_x, tx = rem - rb * P.tiles_x;
       const int y0 = rb * P.R, x0 = tx * P.TW;
       unsigned char* Us = ring + (size_t)s * P.stage_bytes;
       unsigned char* Gs = Us + P.u_bytes;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
+      // register-path rows: the loads of the first two items of this warp are issued before the
+      // ring slot is known to be free (they only read global memory)
+      constexpr int WB_BATCH = 2;
+      WbRow rows[WB_BATCH];
+      const int n_items = items_u + items_g;
+      auto issue = [&](int it, WbRow& row) {
+        if (it < items_u) {
+          const int k = it / (P.R + 2), r = it - k * (P.R + 2);
+          wb_issue<0>(P, b, plane0 + k, y0 - 1 + r, x0 - 1, P.TWu, lane, row);
+        } else if (it < n_items) {
+          const int i2 = it - items_u, k = i2 / P.R, r = i2 - k * P.R;
+          wb_issue<1>(P, b, k, y0 + r, x0, P.TW, lane, row);
+        }
+      };
+      auto commit = [&](int it, const WbRow& row) {
+        if (it < items_u) {
+          const int k = it / (P.R + 2), r = it - k * (P.R + 2);
+          wb_commit<0>(P, y0 - 1 + r, x0 - 1, P.TWu,
+                       reinterpret_cast<uint4*>(Us + (size_t)k * P.sbo_u + (size_t)r * u_row_bytes), lane, row);
+        } else if (it < n_items) {
+          const int i2 = it - items_u, k = i2 / P.R, r = i2 - k * P.R;
+          wb_commit<1>(P, y0 + r, x0, P.TW,
+                       reinterpret_cast<uint4*>(Gs + (size_t)k * P.sbo_g + (size_t)r * g_row_bytes), lane, row);
+        }
+      };
+#pragma unroll
+      for (int j = 0; j < WB_BATCH; ++j) issue(warp + j * WB_LOAD_WARPS, rows[j]);
+      long long t_a = 0, t_b = 0, t_c = 0;
+      if (P.dbg) t_a = clock64();
+      if (P.poll_all) mbar_wait_all(&empty_bar[s], ph ^ 1u); else mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (P.dbg) t_b = clock64();
       if (warp == 0 && tx_bytes) {
         if (elect_one()) {
           mbar_expect_tx(&full_bar[s], tx_bytes);
@@ -189,29 +237,32 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
         }
         __syncwarp();
       }
-      for (int it = warp; it < items_u; it += WB_LOAD_WARPS) {
-        const int k = it / (P.R + 2), r = it - k * (P.R + 2);
-        wb_row<0>(P, b, plane0 + k, y0 - 1 + r, x0 - 1, P.TWu,
-                  reinterpret_cast<uint4*>(Us + (size_t)k * P.sbo_u + (size_t)r * u_row_bytes), lane);
+#pragma unroll
+      for (int j = 0; j < WB_BATCH; ++j) commit(warp + j * WB_LOAD_WARPS, rows[j]);
+      for (int it0 = warp + WB_BATCH * WB_LOAD_WARPS; it0 < n_items; it0 += WB_BATCH * WB_LOAD_WARPS) {
+#pragma unroll
+        for (int j = 0; j < WB_BATCH; ++j) issue(it0 + j * WB_LOAD_WARPS, rows[j]);
+#pragma unroll
+        for (int j = 0; j < WB_BATCH; ++j) commit(it0 + j * WB_LOAD_WARPS, rows[j]);
       }
-      for (int it = warp; it < items_g; it += WB_LOAD_WARPS) {
-        const int k = it / P.R, r = it - k * P.R;
-        wb_row<1>(P, b, k, y0 + r, x0, P.TW,
-                  reinterpret_cast<uint4*>(Gs + (size_t)k * P.sbo_g + (size_t)r * g_row_bytes), lane);
-      }
+      if (P.dbg) t_c = clock64();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (P.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_n < 256) {
+        long long* d = P.dbg + 4 * dbg_n++;
+        d[0] = t_a; d[1] = t_b; d[2] = t_c; d[3] = clock64();
+      }
       if (++s == S) { s = 0; ph ^= 1u; }
     }
   } else {
     // =============================== MMA issuer ===============================================
-    const uint32_t idesc = umma_idesc_bf16(P.M, P.N, 1, 1);
-    const uint64_t a_hi = umma_desc(0u, 128u, (uint32_t)P.sbo_u);
-    const uint64_t b_hi = umma_desc(0u, 128u, (uint32_t)P.sbo_g);
+    const uint32_t idesc = P.idesc;
+    const uint64_t a_hi = P.a_hi, b_hi = P.b_hi;
     int s = 0;
     uint32_t ph = 0;
-    uint32_t acc = 0;                           // 0 until the accumulators hold a value
+    const uint32_t TWu = (uint32_t)P.TWu, TW = (uint32_t)P.TW;
+    int dbg_m = 0;
     for (int tile = split; tile < P.n_tiles; tile += P.splits) {
       const int b = tile / per_img, rem = tile - b * per_img;
       const int rb = rem / P.tiles_x, tx = rem - rb * P.tiles_x;
@@ -219,29 +270,50 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
       const int rows = (P.H - y0) < P.R ? (P.H - y0) : P.R;
       const int wpx = (P.W - x0) < P.TW ? (P.W - x0) : P.TW;
       const int ksteps = (wpx + 15) >> 4;
+      const bool first_tile = tile == split;     // the accumulators hold nothing yet
       (void)b;
-      mbar_wait(&full_bar[s], ph);
+      long long t_a = 0, t_b = 0;
+      if (P.dbg) t_a = clock64();
+      if (P.poll_all) mbar_wait_all(&full_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+      if (P.dbg) t_b = clock64();
       tc_fence_after();
       if (elect_one()) {
         const uint32_t u_lo = smem_u32(ring + (size_t)s * P.stage_bytes) >> 4;
         const uint32_t g_lo = u_lo + (uint32_t)(P.u_bytes >> 4);
+        // Taps innermost: consecutive MMAs go to different accumulators (MMAs into the same TMEM
+        // columns serialise on the accumulate latency).  The issuing thread keeps one RUNNING
+        // 64-bit descriptor per tap and advances it by 16 pixels per K step, so that no MMA waits
+        // on an address computation: a dependent chain of uniform-datapath instructions per MMA
+        // (indexed constant load -> add -> mask -> add) cost ~70 clk per MMA in the first version
+        // (role timeline, profiles/r2_summary.md).  Start addresses stay below 2^14 16-byte units
+        // (228 KB of shared memory), so the descriptor's address field never overflows.
+        uint64_t ad[9];
+#pragma unroll
+        for (int tl = 0; tl < 9; ++tl) ad[tl] = a_hi + (uint64_t)(u_lo + (uint32_t)P.toff[tap0 + tl]);
+        uint64_t bd = b_hi + (uint64_t)g_lo;
+        const uint64_t a_skip = (uint64_t)(TWu - 16u * (uint32_t)ksteps), b_skip = (uint64_t)(TW - 16u * (uint32_t)ksteps);
+        uint32_t accf = first_tile ? 0u : 1u;
         for (int r = 0; r < rows; ++r) {
           for (int kx = 0; kx < ksteps; ++kx) {
-            const uint32_t gt = g_lo + (uint32_t)(r * P.TW + 16 * kx);
-            const uint64_t bd = b_hi | (uint64_t)(gt & 0x3fffu);
-            for (int tl = 0; tl < ntaps; ++tl) {
-              const int tap = tap0 + tl;
-              const int dy = tap / 3, dx = tap - 3 * dy;
-              const uint32_t ut = u_lo + (uint32_t)((r + dy) * P.TWu + 16 * kx + dx);
-              umma_f16(tmem_base + (uint32_t)(tl * P.N), a_hi | (uint64_t)(ut & 0x3fffu), bd, idesc, acc);
-            }
-            acc = 1u;
+#pragma unroll
+            for (int tl = 0; tl < 9; ++tl)
+              if (tl < ntaps) umma_f16(tmem_base + (uint32_t)(tl * P.N), ad[tl], bd, idesc, accf);
+#pragma unroll
+            for (int tl = 0; tl < 9; ++tl) ad[tl] += 16u;
+            bd += 16u;
+            accf = 1u;
           }
+#pragma unroll
+          for (int tl = 0; tl < 9; ++tl) ad[tl] += a_skip;
+          bd += b_skip;
         }
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
-      acc = 1u;
+      if (P.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 256) {
+        long long* d = P.dbg + 1024 + 4 * dbg_m++;
+        d[0] = t_a; d[1] = t_b; d[2] = clock64(); d[3] = (long long)rows * ksteps * ntaps;
+      }
       if (++s == S) { s = 0; ph ^= 1u; }
     }
     if (elect_one()) umma_commit(&done_bar);
@@ -253,7 +325,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
     mbar_wait(&done_bar, 0);
     tc_fence_after();
     const int q = warp & 3, part = warp >> 2;
-    constexpr int PARTS = WB_LOAD_WARPS / 4;
+    const int PARTS = WB_LOAD_WARPS / 4;
     const int m = P.M == 64 ? (lane < 16 ? 16 * q + lane : -1) : 32 * q + lane;
     float* out = P.partial + (size_t)split * (P.wsize + P.cout_pad);
     const int ci = 8 * plane0 + m;
@@ -351,6 +423,11 @@ static bool wgrad_bf16_plan(WgBfParams& P, int sm_count) {
   if (bestS == 2 && 3 * stage_bytes(bestR) + slack(bestR) + 128 <= WB_SMEM_BUDGET) P.n_stages = 3;
   P.sbo_u = (int)(((long long)(P.R + 2) * P.TWu * 16 + 127) / 128 * 128);
   P.sbo_g = P.R * P.TW * 16;
+  for (int t = 0; t < 12; ++t) P.toff[t] = t < 9 ? (t / 3) * P.TWu + (t % 3) : 0;
+  P.idesc = umma_idesc_bf16(P.M, P.N, 1, 1);
+  // no-swizzle descriptors (umma_desc with a zero start address): LBO = 128 B, SBO = plane stride
+  P.a_hi = ((unsigned long long)(128u >> 4) << 16) | ((unsigned long long)((unsigned)P.sbo_u >> 4) << 32) | (1ull << 46);
+  P.b_hi = ((unsigned long long)(128u >> 4) << 16) | ((unsigned long long)((unsigned)P.sbo_g >> 4) << 32) | (1ull << 46);
   P.u_bytes = P.u_alloc * P.sbo_u;
   P.stage_bytes = (int)stage_bytes(P.R);
   P.n_row_blocks = (P.H + P.R - 1) / P.R;
@@ -455,9 +532,45 @@ extern "C" int dincae_conv3x3_wgrad_bf16(const void* src0, int c0p, int src0_hal
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)P.n_stages * P.stage_bytes + (size_t)(P.slots - P.u_alloc) * P.sbo_u + 128;
-  launch_k(conv3x3_wgrad_bf16_kernel, P.jobs * P.splits, WB_THREADS, smem, st, P, tmu0, tmu1, tmg);
+  {
+    static int lw = 0, pa = -1;
+    if (pa < 0) {
+      const char* e = getenv("DINCAE_WB_WARPS");
+      lw = e ? atoi(e) : 16;
+      if (lw != 4 && lw != 8 && lw != 12 && lw != 16) lw = 16;
+      e = getenv("DINCAE_WB_POLL_ALL");
+      pa = (e && e[0] == '1') ? 1 : 0;
+    }
+    P.load_warps = lw;
+    P.poll_all = pa;
+  }
+  static long long* dbg_dev = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("DINCAE_WB_DEBUG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
+  }
+  P.dbg = nullptr;
+  if (dbg_on) {
+    cudaMemsetAsync(dbg_dev, 0, 2048 * sizeof(long long), st);
+    P.dbg = dbg_dev;
+  }
+  launch_k(conv3x3_wgrad_bf16_kernel, P.jobs * P.splits, 32 * (P.load_warps + 1), smem, st, P, tmu0, tmu1, tmg);
   int rc = check_launch();
   if (rc) return rc;
+  if (dbg_on) {
+    static long long h[2048];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "wgrad_bf16 timeline CTA0: M=%d N=%d R=%d TW=%d stages=%d jobs=%d splits=%d tiles=%d\n", P.M, P.N,
+            P.R, P.TW, P.n_stages, P.jobs, P.splits, P.n_tiles);
+    const long long t0 = h[0];
+    for (int i = 0; i < 12 && h[4 * i]; ++i)
+      fprintf(stderr, "  load %2d: wait_empty %7lld..%7lld  stored %7lld  arrived %7lld | mma: wait_full %7lld..%7lld issued %7lld (%lld mmas)\n",
+              i, h[4 * i] - t0, h[4 * i + 1] - t0, h[4 * i + 2] - t0, h[4 * i + 3] - t0, h[1024 + 4 * i] - t0,
+              h[1024 + 4 * i + 1] - t0, h[1024 + 4 * i + 2] - t0, h[1024 + 4 * i + 3]);
+  }
   int gp4 = 2 * gp;
   if (gp4 * 4 > cout_pad) gp4 = cout_pad / 4;
   return dincae_conv3x3_wgrad_reduce(workspace, P.splits, cinp4, gp4, cout_pad, dw, db, stream);

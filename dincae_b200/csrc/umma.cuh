@@ -29,11 +29,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Wait for a phase of an mbarrier.  Called by ALL lanes of a converged warp; only lane 0 polls
+// (32 lanes polling the same barrier word are 32 shared-memory transactions per try, and the
+// waiting roles of the tcgen05 kernels took ~45 % of the shared-memory pipe away from the tensor
+// cores' operand reads that way: profiles/r2_summary.md), the others park at the warp barrier.
+// backoff_ns > 0: sleep between polls (roles that run far ahead of their consumer).
+// every lane polls (the round-1 behaviour; kept for A/B measurements)
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();      // never hang the device on a lost arrive
+    if (++spins > (1u << 24)) __trap();
   }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      if (backoff_ns) __nanosleep(backoff_ns);
+      if (++spins > (1u << 24)) __trap();    // never hang the device on a lost arrive
+    }
+  }
+  __syncwarp();
 }
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, version 1)

@@ -7,7 +7,8 @@ from dincae_b200.data import DeviceCube
 from dincae_b200.engine import Plan
 from dincae_b200.sampler import TrainSampler
 from dincae_b200.trainer import Trainer, Reconstructor
-T, H, W, B = 12, 512, 512, int(sys.argv[1]) if len(sys.argv) > 1 else 4
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+T, H, W = max(12, B + 4), 512, 512
 LANES = 8 if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else 4
 fields, missing = [], []
 for k in range(4):

@@ -1,4 +1,4 @@
-// Microbenchmark: cycles per tcgen05.mma kind::tf32 (M=128|64, K=8) issued by one thread,
+// Microbenchmark: cycles per tcgen05.mma kind::f16 with bf16 operands (M=128|64, K=16) issued by one thread,
 // operands in shared memory, no-swizzle descriptors with the strides the conv kernels use.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_bench umma_bench.cu && ./umma_bench
 #include <cstdio>
@@ -39,9 +39,7 @@ __global__ void __launch_bounds__(128) bench_kernel(Cfg c, long long* out) {
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
   if (warp == 0 && elect_one()) {
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)c.a_mn << 15) |
-                           ((uint32_t)c.b_mn << 16) | ((uint32_t)(c.N >> 3) << 17) |
-                           ((uint32_t)(c.M >> 4) << 24);
+    const uint32_t idesc = umma_idesc_bf16(c.M, c.N, c.a_mn, c.b_mn);
     const uint64_t a0 = umma_desc(smem_u32(smem), c.a_lbo, c.a_sbo);
     const uint64_t b0 = umma_desc(smem_u32(smem + 128 * 1024), c.b_lbo, c.b_sbo);
     uint32_t phase = 0;
@@ -52,7 +50,7 @@ __global__ void __launch_bounds__(128) bench_kernel(Cfg c, long long* out) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const uint32_t d = tmem + (uint32_t)((u & (c.n_acc - 1)) * c.N);
-          umma_tf32(d, a0 + sh + (uint32_t)(u * c.shift_units), b0, idesc, 1u);
+          umma_f16(d, a0 + sh + (uint32_t)(u * c.shift_units), b0, idesc, 1u);
         }
         sh = (sh + 8 * c.shift_units) & 1023;
       }
@@ -76,32 +74,23 @@ int main() {
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   // name, cfg
   struct Named { const char* name; Cfg c; } cases[] = {
-      {"fwd  M128 N16  sbo128  (linear tile)", {128, 16, 0, 0, 128, 20000, 128, 256, 4096, 1, 8}},
-      {"fwd  M128 N16  sbo1824 (114-px rows)", {128, 16, 0, 0, 1824, 20000, 128, 256, 4096, 1, 8}},
-      {"fwd  M128 N16  sbo928  (58-px rows)", {128, 16, 0, 0, 928, 20000, 128, 256, 4096, 1, 8}},
-      {"fwd  M128 N16  sbo1024 (64-px rows)", {128, 16, 0, 0, 1024, 20000, 128, 256, 4096, 1, 8}},
-      {"fwd  M128 N32  sbo1824", {128, 32, 0, 0, 1824, 20000, 128, 512, 4096, 1, 8}},
-      {"fwd  M128 N48  sbo1824", {128, 48, 0, 0, 1824, 20000, 128, 768, 4096, 1, 8}},
-      {"fwd  M128 N64  sbo1824", {128, 64, 0, 0, 1824, 20000, 128, 1024, 4096, 1, 8}},
-      {"fwd  M128 N128 sbo1824", {128, 128, 0, 0, 1824, 20000, 128, 2048, 4096, 1, 4}},
-      {"fwd  M128 N256 sbo1824", {128, 256, 0, 0, 1824, 20000, 128, 4096, 4096, 1, 2}},
-      {"fwd  M64  N16  sbo1824", {64, 16, 0, 0, 1824, 20000, 128, 256, 4096, 1, 8}},
-      {"fwd  M128 N16  same acc", {128, 16, 0, 0, 1824, 20000, 128, 256, 4096, 1, 1}},
-      {"fwd  M128 N16  no shift", {128, 16, 0, 0, 1824, 20000, 128, 256, 4096, 0, 8}},
-      {"dgr  M128 N16  B mn-major", {128, 16, 0, 1, 1824, 20000, 256, 128, 4096, 1, 8}},
-      {"dgr  M128 N96  B mn-major", {128, 96, 0, 1, 1824, 20000, 768, 128, 4096, 1, 4}},
-      {"wgr  M128 N16  A,B mn-major sbo1824", {128, 16, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
-      {"wgr  M64  N16  A,B mn-major sbo1824", {64, 16, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
-      {"wgr  M128 N64  A,B mn-major sbo1824", {128, 64, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
-      {"wgr  M64  N64  A,B mn-major sbo1824", {64, 64, 1, 1, 1824, 128, 928, 128, 4096, 1, 2}},
-      // K-major transposed tiles of the weight gradient: 144-byte core-matrix pitch (bank pad)
-      // vs 128-byte aligned core matrices; shift = one K step (2 pixel groups)
-      {"wgK  M64  N48  K-major sbo144 lbo304/880", {64, 48, 0, 0, 144, 304, 144, 880, 4096, 38, 1}},
-      {"wgK  M64  N48  K-major sbo128 lbo256/768", {64, 48, 0, 0, 128, 256, 128, 768, 4096, 32, 1}},
-      {"wgK  M64  N24  K-major sbo144 lbo592/432", {64, 24, 0, 0, 144, 592, 144, 432, 4096, 74, 1}},
-      {"wgK  M64  N24  K-major sbo128 lbo512/384", {64, 24, 0, 0, 128, 512, 128, 384, 4096, 64, 1}},
-      {"wgK  M128 N120 K-major sbo144 lbo1744", {128, 120, 0, 0, 144, 1744, 144, 2176, 4096, 218, 1}},
-      {"wgK  M128 N120 K-major sbo128 lbo1536", {128, 120, 0, 0, 128, 1536, 128, 1920, 4096, 192, 1}},
+      // forward: A = pixels K-major (SBO = row pitch, LBO = plane stride), B = weights K-major
+      {"fwd  M128 N32  K-major", {128, 32, 0, 0, 928, 20000, 128, 512, 4096, 1, 8}},
+      {"fwd  M128 N48  K-major", {128, 48, 0, 0, 928, 20000, 128, 768, 4096, 1, 8}},
+      {"fwd  M128 N64  K-major", {128, 64, 0, 0, 928, 20000, 128, 1024, 4096, 1, 8}},
+      {"fwd  M128 N128 K-major", {128, 128, 0, 0, 928, 20000, 128, 2048, 4096, 1, 4}},
+      // weight gradient: both operands MN-major (channels contiguous), LBO = 128 B, SBO = plane stride
+      {"wgr  M64  N32  A,B MN-major sbo 10624/8192", {64, 32, 1, 1, 10624, 128, 8192, 128, 4096, 1, 8}},
+      {"wgr  M128 N32  A,B MN-major", {128, 32, 1, 1, 7424, 128, 5120, 128, 4096, 1, 8}},
+      {"wgr  M128 N16  A,B MN-major", {128, 16, 1, 1, 7424, 128, 5120, 128, 4096, 1, 8}},
+      {"wgr  M128 N64  A,B MN-major", {128, 64, 1, 1, 7424, 128, 2048, 128, 4096, 1, 8}},
+      {"wgr  M128 N128 A,B MN-major", {128, 128, 1, 1, 7424, 128, 2048, 128, 4096, 1, 4}},
+      {"wgr  M64  N32  A MN, B K-major", {64, 32, 1, 0, 10624, 128, 128, 512, 4096, 1, 8}},
+      {"wgr  M64  N32  A K,  B MN-major", {64, 32, 0, 1, 928, 20000, 8192, 128, 4096, 1, 8}},
+      {"wgr  M64  N32  A,B MN-major sbo 10752 (128-B aligned +128)", {64, 32, 1, 1, 10752, 128, 8320, 128, 4096, 1, 8}},
+      {"wgr  M64  N32  A,B MN-major sbo 144/144 (packed planes)", {64, 32, 1, 1, 144, 2048, 144, 2048, 4096, 0, 8}},
+      {"wgr  M64  N32  A,B MN-major lbo/sbo swapped (sbo 128, lbo 10624)", {64, 32, 1, 1, 128, 10624, 128, 8192, 4096, 1, 8}},
+      {"wgr  M64  N32  A,B MN-major same acc", {64, 32, 1, 1, 10624, 128, 8192, 128, 4096, 1, 1}},
   };
   for (auto& nc : cases) {
     for (int grid : {1, 148}) {
