@@ -9,7 +9,7 @@ from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int6
                     c_uint16, c_uint64, c_uint8, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdincae_b200.so")
+LIB_PATH = os.environ.get("DINCAE_LIB") or os.path.join(_HERE, "libdincae_b200.so")   # DINCAE_LIB: A/B builds
 
 _lib = None
 

@@ -473,6 +473,11 @@ def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size, rank=0
         writer.write_records(offset, buf.numpy().reshape(-1).view(np.uint8), n)
 
     futures = [None] * nslots
+    if getattr(recon, "use_graph", False):
+        # graphs of every batch size of this range (full batches + the tail) are captured before
+        # the writer threads start: a capture must not overlap their event waits
+        for n in sorted({min(test_len, (ii + 1) * batch_size) - ii * batch_size for ii in range(b0, b1)}):
+            recon.capture(n)
     try:
         with ThreadPoolExecutor(max_workers=_SAVE_THREADS) as pool:
             for k, ii in enumerate(range(b0, b1)):

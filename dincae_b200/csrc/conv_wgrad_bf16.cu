@@ -219,7 +219,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
       for (int j = 0; j < WB_BATCH; ++j) issue(warp + j * WB_LOAD_WARPS, rows[j]);
       long long t_a = 0, t_b = 0, t_c = 0;
       if (P.dbg) t_a = clock64();
-      if (P.poll_all) mbar_wait_all(&empty_bar[s], ph ^ 1u); else mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (P.poll_all) mbar_wait(&empty_bar[s], ph ^ 1u); else mbar_wait_lane0(&empty_bar[s], ph ^ 1u);
       if (P.dbg) t_b = clock64();
       if (warp == 0 && tx_bytes) {
         if (elect_one()) {
@@ -274,7 +274,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
       (void)b;
       long long t_a = 0, t_b = 0;
       if (P.dbg) t_a = clock64();
-      if (P.poll_all) mbar_wait_all(&full_bar[s], ph); else mbar_wait(&full_bar[s], ph);
+      if (P.poll_all) mbar_wait(&full_bar[s], ph); else mbar_wait_lane0(&full_bar[s], ph);
       if (P.dbg) t_b = clock64();
       tc_fence_after();
       if (elect_one()) {
@@ -539,7 +539,7 @@ extern "C" int dincae_conv3x3_wgrad_bf16(const void* src0, int c0p, int src0_hal
       lw = e ? atoi(e) : 16;
       if (lw != 4 && lw != 8 && lw != 12 && lw != 16) lw = 16;
       e = getenv("DINCAE_WB_POLL_ALL");
-      pa = (e && e[0] == '1') ? 1 : 0;
+      pa = (e && e[0] == '0') ? 0 : 1;
     }
     P.load_warps = lw;
     P.poll_all = pa;

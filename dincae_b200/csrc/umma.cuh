@@ -29,25 +29,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Wait for a phase of an mbarrier.  Called by ALL lanes of a converged warp; only lane 0 polls
-// (32 lanes polling the same barrier word are 32 shared-memory transactions per try, and the
-// waiting roles of the tcgen05 kernels took ~45 % of the shared-memory pipe away from the tensor
-// cores' operand reads that way: profiles/r2_summary.md), the others park at the warp barrier.
-// backoff_ns > 0: sleep between polls (roles that run far ahead of their consumer).
-// every lane polls (the round-1 behaviour; kept for A/B measurements)
-__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+// Wait for a phase of an mbarrier: every lane of the (converged) warp polls.  Measured against
+// a lane-0-only poll + __syncwarp (profiles/r2_summary.md): the single-lane variant takes the
+// polling traffic off the shared-memory pipe but wakes the warp up later, and the config-A step
+// (many short kernels) was 6.7 % slower with it (0.736 vs 0.690 ms); the bf16 kernels at 512x512
+// did not change.  So: all lanes poll.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 24)) __trap();      // never hang the device on a lost arrive
   }
 }
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0) {
+// lane 0 polls, the other lanes park at the warp barrier (kept for A/B measurements)
+__device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-      if (backoff_ns) __nanosleep(backoff_ns);
-      if (++spins > (1u << 24)) __trap();    // never hang the device on a lost arrive
+      if (++spins > (1u << 24)) __trap();
     }
   }
   __syncwarp();

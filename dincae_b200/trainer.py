@@ -94,7 +94,9 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: CUDA calls of other host threads (writer threads waiting on events)
+            # must not invalidate this capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 fn()
             self._graphs[key] = g
         g.replay()
@@ -240,6 +242,23 @@ class Reconstructor:
         self.out_dev[0, :n].copy_(net.m_rec[:n])
         self.out_dev[1, :n].copy_(net.s2_rec[:n])
 
+    def capture(self, n):
+        """CUDA graph of the sweep of a batch of ``n`` frames (captured on first use; callers that
+        run host threads next to the sweep capture the sizes they need up front)."""
+        g = self._graphs.get(n)
+        if g is None:
+            s = torch.cuda.Stream(device=self.cube.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue(n)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._enqueue(n)
+            self._graphs[n] = g
+        return g
+
     def run_batch(self, frames, slot=0):
         """frames: int array (n <= B).  Returns pinned host tensor [2,B,H,W] (valid after a
         stream sync): [0] = m_rec, [1] = sigma2_rec -- or, in records mode, the int32 view of
@@ -264,19 +283,7 @@ class Reconstructor:
         ev.record()
         self._idx_events[islot] = ev
         if self.use_graph:
-            g = self._graphs.get(n)
-            if g is None:
-                s = torch.cuda.Stream(device=self.cube.dev)
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    self._enqueue(n)
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue(n)
-                self._graphs[n] = g
-            g.replay()
+            self.capture(n).replay()
         else:
             self._enqueue(n)
         out = self.out_host[slot]

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) bench_kernel(Cfg c, long long* out) {
       }
       const long long t1 = clock64();
       umma_commit(&bar);
-      mbar_wait_all(&bar, phase);
+      mbar_wait(&bar, phase);
       phase ^= 1;
       const long long t2 = clock64();
       if (blockIdx.x == 0) { out[2 * rep] = t1 - t0; out[2 * rep + 1] = t2 - t0; }
