@@ -56,6 +56,19 @@ SIGNATURES = {
     "dincae_dense_fwd": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_weight": (c_int, [vp, vp, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_dense_factored_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "dincae_dense_factored_sumsq": (c_int, [vp, c_size_t, c_int, vp, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                            vp, vp, c_size_t, vp]),
+    "dincae_adam_update_factored": (c_int, [vp, vp, vp, c_int, vp, c_size_t, c_int, vp, c_size_t, c_int,
+                                            c_int, c_int, c_int, c_int, c_float, vp, c_float, c_float, c_float,
+                                            vp, vp]),
+    "dincae_dense_factored_expand": (c_int, [vp, c_size_t, c_int, vp, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                             vp, c_int, vp]),
+    "dincae_dense_bias_grad": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+    "dincae_adam_multi_workspace": (c_size_t, [c_size_t]),
+    "dincae_adam_step_multi": (c_int, [vp, vp, c_size_t, c_int, vp, vp, c_size_t, c_float, vp, c_float, c_float,
+                                       c_float, c_float, vp, vp, vp, vp, c_size_t, vp]),
+    "dincae_sum_ranks_f64": (c_int, [vp, c_size_t, c_int, c_int, vp, vp]),
     "dincae_head_recon": (c_int, [vp, c_int, c_int, c_int, vp, vp, vp]),
     "dincae_head_recon_records": (c_int, [vp, c_int, c_int, c_int, vp, vp, c_float, c_int, c_int, vp, vp]),
     "dincae_head_loss_workspace": (c_size_t, [c_int, c_int, c_int]),

@@ -1,0 +1,456 @@
+// Dense-bottleneck weight gradients kept in FACTORED form (new capability; replaces the
+// materialised MatMul gradient + ApplyAdam of DINCAE/__init__.py:479-483, 598-603).
+//
+// The gradient of a dense kernel is a rank-B outer product, dW = x^T dz with x [Bt,K] the layer's
+// input and dz [Bt,N] the gradient of its pre-activation (Bt = frames of the GLOBAL batch).  At
+// BASELINE configs[3] the two dense kernels hold 688 M of the 689 M parameters: writing dW, reading
+// it twice (global norm, Adam) and -- data parallel -- all-reducing 2.75 GB per step is what the
+// step costs.  Instead:
+//   * ||dW||_F^2 = sum_{b,b'} (x_b . x_b') (dz_b . dz_b')   (two Bt x Bt Gram matrices) goes into
+//     the global norm of tf.clip_by_global_norm without forming dW;
+//   * the Adam kernel recomputes its tile of dW from the factors (Bt FMAs per weight) while it
+//     streams p, m, v: 24 bytes per parameter instead of 36 (write dW, read it twice);
+//   * data-parallel ranks exchange the FACTORS (an all-gather of Bt x (K+N) floats) instead of
+//     all-reducing dW; every rank then applies the same update in the same order.
+// Rows of the factors live in `world` per-rank blocks (row bt -> rank bt / rows_per_rank): the
+// all-gathered buffer is used in place.
+#include "common.cuh"
+#include "umma.cuh"
+#include <math.h>
+
+namespace dincae {
+
+struct Factor {
+  const float* base;       // row (r, i) at base + r * rank_stride + i * ld
+  size_t rank_stride;      // floats between the blocks of consecutive ranks
+  int ld;                  // floats between consecutive rows of a rank
+};
+
+__device__ __forceinline__ const float* factor_row(const Factor& f, int bt, int rows_per_rank) {
+  const int r = bt / rows_per_rank;
+  return f.base + (size_t)r * f.rank_stride + (size_t)(bt - r * rows_per_rank) * f.ld;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram matrices: partial[which][c][b][b'] = sum over the columns of chunk c of f[b][k] f[b'][k].
+// grid (chunks, 2, pair tiles): y = 0 -> x (K columns), y = 1 -> dz (N columns); a CTA owns a
+// 64 x 64 tile of (b, b') pairs, a thread 4 x 4 of them.
+// ---------------------------------------------------------------------------------------------
+constexpr int GR_COLS = 32;       // columns staged per pass
+constexpr int GR_TILE = 64;       // rows per pair-tile side
+constexpr int GR_MAX_BT = 1024;
+
+__global__ void __launch_bounds__(256) gram_partial_kernel(Factor fx, Factor fz, int Bt, int rows_per_rank,
+                                                           int K, int N, int cols_per_cta,
+                                                           float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float ga[GR_TILE][GR_COLS + 1];
+  __shared__ float gb[GR_TILE][GR_COLS + 1];
+  const Factor f = blockIdx.y == 0 ? fx : fz;
+  const int ncols = blockIdx.y == 0 ? K : N;
+  const int c0 = blockIdx.x * cols_per_cta;
+  const int nt = (Bt + GR_TILE - 1) / GR_TILE;
+  const int ta = blockIdx.z / nt, tb = blockIdx.z - ta * nt;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int c1 = min(ncols, c0 + cols_per_cta);
+  for (int cc = c0; cc < c1; cc += GR_COLS) {
+    const int w = min(GR_COLS, c1 - cc);
+    for (int i = tid; i < GR_TILE * GR_COLS; i += 256) {
+      const int r = i / GR_COLS, c = i - r * GR_COLS;
+      const int ba = ta * GR_TILE + r, bb = tb * GR_TILE + r;
+      ga[r][c] = (c < w && ba < Bt) ? __ldg(factor_row(f, ba, rows_per_rank) + cc + c) : 0.f;
+      gb[r][c] = (c < w && bb < Bt) ? __ldg(factor_row(f, bb, rows_per_rank) + cc + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < GR_COLS; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = ga[ty + 16 * i][c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = gb[tx + 16 * j][c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)Bt * Bt;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ba = ta * GR_TILE + ty + 16 * i, bb = tb * GR_TILE + tx + 16 * j;
+      if (ba < Bt && bb < Bt) out[(size_t)ba * Bt + bb] = c0 < ncols ? acc[i][j] : 0.f;
+    }
+}
+
+// sumsq[0] += sum over pairs of Gx[pair] * Gz[pair], the Gram entries summed over the chunk
+// partials in a fixed order (one CTA; deterministic).
+__global__ void __launch_bounds__(1024) gram_finish_kernel(const float* __restrict__ partial, int chunks_x,
+                                                           int chunks_z, int chunks_stride, int npairs,
+                                                           double* __restrict__ sumsq) {
+  pdl_trigger();
+  pdl_wait();
+  double mine = 0.0;
+  for (int pr = threadIdx.x; pr < npairs; pr += blockDim.x) {
+    double gx = 0.0, gz = 0.0;
+    for (int c = 0; c < chunks_x; ++c) gx += (double)partial[(size_t)c * npairs + pr];
+    for (int c = 0; c < chunks_z; ++c) gz += (double)partial[((size_t)chunks_stride + c) * npairs + pr];
+    mine += gx * gz;
+  }
+  mine = warp_sum(mine);
+  __shared__ double red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    sumsq[0] += t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam update of a dense kernel w [K][ldw] (N columns used) from its gradient factors.
+// grid (ceil(N/256), ceil(K/32)); thread = 8 rows x 4 columns (the tiling of outer_kernel).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_factored_kernel(float* __restrict__ w, float* __restrict__ m,
+                                                            float* __restrict__ v, int ldw, Factor fx, Factor fz,
+                                                            int Bt, int rows_per_rank, int K, int N,
+                                                            float grad_scale, const double* __restrict__ denom,
+                                                            float beta1, float beta2, float eps,
+                                                            const float* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float xs[16][32];
+  __shared__ __align__(16) float zs[16][256];
+  const int tid = threadIdx.x, tn = tid & 63, tk = tid >> 6;
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 256;
+  const int n = n0 + 4 * tn;
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = f4_zero();
+  for (int b0 = 0; b0 < Bt; b0 += 16) {
+    if (tid < 128) {
+      const int bb = tid >> 3, c = tid & 7;
+      const int k = k0 + 4 * c;
+      const bool ok = b0 + bb < Bt && k < K;
+      const float* row = ok ? factor_row(fx, b0 + bb, rows_per_rank) : fx.base;
+      *reinterpret_cast<float4*>(&xs[bb][4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + k), ok);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + 256 * r;
+      const int bb = idx >> 6, c = idx & 63;
+      const int nn = n0 + 4 * c;
+      const bool ok = b0 + bb < Bt && nn < N;
+      const float* row = ok ? factor_row(fz, b0 + bb, rows_per_rank) : fz.base;
+      *reinterpret_cast<float4*>(&zs[bb][4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + nn), ok);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int bb = 0; bb < 16; ++bb) {
+      const float4 zv = *reinterpret_cast<const float4*>(&zs[bb][4 * tn]);
+      const float4 x0 = *reinterpret_cast<const float4*>(&xs[bb][8 * tk]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&xs[bb][8 * tk + 4]);
+      acc[0] = f4_fma(x0.x, zv, acc[0]); acc[1] = f4_fma(x0.y, zv, acc[1]);
+      acc[2] = f4_fma(x0.z, zv, acc[2]); acc[3] = f4_fma(x0.w, zv, acc[3]);
+      acc[4] = f4_fma(x1.x, zv, acc[4]); acc[5] = f4_fma(x1.y, zv, acc[5]);
+      acc[6] = f4_fma(x1.z, zv, acc[6]); acc[7] = f4_fma(x1.w, zv, acc[7]);
+    }
+    __syncthreads();
+  }
+  if (n >= N) return;
+  if (denom) grad_scale /= (float)(*denom);
+  const float gs = grad_scale * state[4];            // 1/n normalisation times the clip scale
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  // all loads of the thread's rows first, then the arithmetic, then the stores
+  float4 pp[8], mm[8], vv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + 8 * tk + i;
+    const size_t at = (size_t)k * ldw + n;
+    const bool ok = k < K;
+    pp[i] = ok ? *reinterpret_cast<const float4*>(w + at) : f4_zero();
+    mm[i] = ok ? *reinterpret_cast<const float4*>(m + at) : f4_zero();
+    vv[i] = ok ? *reinterpret_cast<const float4*>(v + at) : f4_zero();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float pa[4] = {pp[i].x, pp[i].y, pp[i].z, pp[i].w};
+    float ma[4] = {mm[i].x, mm[i].y, mm[i].z, mm[i].w};
+    float va[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+    const float ga[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float gk = ga[c] * gs;
+      ma[c] = ma[c] + (gk - ma[c]) * omb1;
+      va[c] = va[c] + (gk * gk - va[c]) * omb2;
+      pa[c] = pa[c] - (ma[c] * lr_t) / (sqrtf(va[c]) + eps);
+    }
+    pp[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    mm[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    vv[i] = make_float4(va[0], va[1], va[2], va[3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + 8 * tk + i;
+    if (k < K) {
+      const size_t at = (size_t)k * ldw + n;
+      *reinterpret_cast<float4*>(w + at) = pp[i];
+      *reinterpret_cast<float4*>(m + at) = mm[i];
+      *reinterpret_cast<float4*>(v + at) = vv[i];
+    }
+  }
+}
+
+// dw = x^T dz written out (tests / callers that want the matrix): the same tiling without Adam
+__global__ void __launch_bounds__(256) factored_expand_kernel(float* __restrict__ dw, int ldw, Factor fx, Factor fz,
+                                                              int Bt, int rows_per_rank, int K, int N) {
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.x * 256 + threadIdx.x, k = blockIdx.y;
+  if (n >= N || k >= K) return;
+  float s = 0.f;
+  for (int b = 0; b < Bt; ++b)
+    s = fmaf(__ldg(factor_row(fx, b, rows_per_rank) + k), __ldg(factor_row(fz, b, rows_per_rank) + n), s);
+  dw[(size_t)k * ldw + n] = s;
+}
+
+// out[n] = sum_b dz[b][n] (bias gradient of a dense layer), rows of one rank
+__global__ void __launch_bounds__(256) dense_bias_grad_kernel(const float* __restrict__ dz, int B, int N, int ld,
+                                                              float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += __ldg(dz + (size_t)b * ld + n);
+  db[n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Global norm and Adam over the materialised part of the gradient, given as `world` per-rank
+// copies that are summed on the fly in rank order (an all-gathered buffer used in place; world = 1
+// is the plain case), plus `extra` (device double): sum of squares of the factored gradients.
+// ---------------------------------------------------------------------------------------------
+struct RedWork2 {
+  unsigned int counter;
+  unsigned int pad[3];
+  double partial[1];
+};
+
+static int red2_blocks(size_t n) {
+  size_t b = (n + 4095) / 4096;
+  if (b > 8 * 148) b = 8 * 148;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void __launch_bounds__(256) sumsq_multi_kernel(const float* __restrict__ g, size_t rank_stride, int world,
+                                                          size_t n, float grad_scale, const double* __restrict__ denom,
+                                                          const double* __restrict__ extra, float clip_norm,
+                                                          const float* __restrict__ lr, float beta1, float beta2,
+                                                          float* __restrict__ state, RedWork2* __restrict__ work) {
+  pdl_trigger();
+  pdl_wait();
+  if (denom) grad_scale /= (float)(*denom);
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < world; ++r) a += __ldg(g + (size_t)r * rank_stride + i);
+    s = fmaf(a, a, s);
+  }
+  double d = warp_sum((double)s);
+  __shared__ double red[8];
+  __shared__ bool is_last;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    work->partial[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(&work->counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double mine = 0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) mine += *((volatile double*)&work->partial[b]);
+  mine = warp_sum(mine);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    if (extra) t += *extra;
+    const float norm = (float)(sqrt(t) * (double)grad_scale);
+    float scale = 1.0f;
+    if (clip_norm > 0.f) scale = clip_norm * fminf(1.0f / norm, 1.0f / clip_norm);
+    const float b1p = state[0], b2p = state[1];
+    state[2] = norm;
+    state[3] = (*lr) * sqrtf(1.0f - b2p) / (1.0f - b1p);
+    state[4] = scale;
+    state[0] = b1p * beta1;
+    state[1] = b2p * beta2;
+    work->counter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         size_t rank_stride, int world, float* __restrict__ m,
+                                                         float* __restrict__ v, size_t n, float grad_scale,
+                                                         const double* __restrict__ denom, float beta1, float beta2,
+                                                         float eps, const float* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
+  if (denom) grad_scale /= (float)(*denom);
+  const float gs = grad_scale * state[4];
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < world; ++r) a += __ldg(g + (size_t)r * rank_stride + i);
+    const float gk = a * gs;
+    const float mk = m[i] + (gk - m[i]) * omb1;
+    const float vk = v[i] + (gk * gk - v[i]) * omb2;
+    m[i] = mk;
+    v[i] = vk;
+    p[i] = p[i] - (mk * lr_t) / (sqrtf(vk) + eps);
+  }
+}
+
+// out[k] = sum over ranks of in[r * rank_stride + k] (doubles), k < count: loss sums of all ranks
+__global__ void sum_ranks_f64_kernel(const double* __restrict__ in, size_t rank_stride, int world, int count,
+                                     double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = threadIdx.x;
+  if (k >= count) return;
+  double s = 0.0;
+  for (int r = 0; r < world; ++r) s += in[(size_t)r * rank_stride + k];
+  out[k] = s;
+}
+
+}  // namespace dincae
+
+using namespace dincae;
+
+static int gram_chunks(int ncols, int Bt, int* cols_per_cta) {
+  // about two CTAs per SM over (column chunks x pair tiles); chunks are multiples of GR_COLS columns
+  const int nt = (Bt + GR_TILE - 1) / GR_TILE;
+  int want = (2 * 148) / (nt * nt);
+  if (want < 1) want = 1;
+  int per = (ncols + want - 1) / want;
+  per = (per + GR_COLS - 1) / GR_COLS * GR_COLS;
+  if (per < GR_COLS) per = GR_COLS;
+  *cols_per_cta = per;
+  return (ncols + per - 1) / per;
+}
+
+extern "C" size_t dincae_dense_factored_workspace(int Bt, int K, int N) {
+  if (Bt <= 0 || K <= 0 || N <= 0) return 0;
+  int per;
+  const int wide = K > N ? K : N;
+  const int chunks = gram_chunks(wide, Bt, &per);
+  return align_up((size_t)2 * chunks * Bt * Bt * sizeof(float), 256);
+}
+
+extern "C" int dincae_dense_factored_sumsq(const float* x, size_t x_rank_stride, int ldx,
+                                           const float* dz, size_t dz_rank_stride, int lddz,
+                                           int world, int rows_per_rank, int K, int N, double* sumsq,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  const int Bt = world * rows_per_rank;
+  if (!x || !dz || !sumsq || !workspace || world <= 0 || rows_per_rank <= 0 || K <= 0 || N <= 0) return DINCAE_EINVAL;
+  if (Bt > GR_MAX_BT) return DINCAE_EINVAL;
+  if (workspace_bytes < dincae_dense_factored_workspace(Bt, K, N)) return DINCAE_ENOSPC;
+  int per;
+  const int wide = K > N ? K : N;
+  const int chunks = gram_chunks(wide, Bt, &per);
+  const int chunks_x = (K + per - 1) / per, chunks_z = (N + per - 1) / per;
+  const int nt = (Bt + GR_TILE - 1) / GR_TILE;
+  Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(gram_partial_kernel, dim3(chunks, 2, nt * nt), 256, 0, st, fx, fz, Bt, rows_per_rank, K, N, per,
+           reinterpret_cast<float*>(workspace));
+  int rc = check_launch();
+  if (rc) return rc;
+  launch_k(gram_finish_kernel, 1, 1024, 0, st, reinterpret_cast<const float*>(workspace), chunks_x, chunks_z,
+           chunks, Bt * Bt, sumsq);
+  return check_launch();
+}
+
+extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw,
+                                           const float* x, size_t x_rank_stride, int ldx,
+                                           const float* dz, size_t dz_rank_stride, int lddz,
+                                           int world, int rows_per_rank, int K, int N,
+                                           float grad_scale, const double* denom, float beta1, float beta2,
+                                           float eps, const float* state, void* stream) {
+  if (!w || !m || !v || !x || !dz || !state || world <= 0 || rows_per_rank <= 0 || K <= 0 || N <= 0) return DINCAE_EINVAL;
+  if ((ldw & 3) || (N & 3) || (K & 3) || (ldx & 3) || (lddz & 3) || (x_rank_stride & 3) || (dz_rank_stride & 3) ||
+      (((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)x | (uintptr_t)dz) & 15))
+    return DINCAE_EINVAL;
+  Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
+  launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, 32)), 256, 0, (cudaStream_t)stream, w, m, v, ldw,
+           fx, fz, world * rows_per_rank, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state);
+  return check_launch();
+}
+
+extern "C" int dincae_dense_factored_expand(const float* x, size_t x_rank_stride, int ldx,
+                                            const float* dz, size_t dz_rank_stride, int lddz,
+                                            int world, int rows_per_rank, int K, int N, float* dw, int ldw,
+                                            void* stream) {
+  if (!x || !dz || !dw || world <= 0 || rows_per_rank <= 0 || K <= 0 || N <= 0 || K > 65535) return DINCAE_EINVAL;
+  Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
+  launch_k(factored_expand_kernel, dim3(ceil_div(N, 256), K), 256, 0, (cudaStream_t)stream, dw, ldw, fx, fz,
+           world * rows_per_rank, rows_per_rank, K, N);
+  return check_launch();
+}
+
+extern "C" int dincae_dense_bias_grad(const float* dz, int B, int N, int ld, float* db, void* stream) {
+  if (!dz || !db || B <= 0 || N <= 0) return DINCAE_EINVAL;
+  launch_k(dense_bias_grad_kernel, ceil_div(N, 256), 256, 0, (cudaStream_t)stream, dz, B, N, ld, db);
+  return check_launch();
+}
+
+extern "C" size_t dincae_adam_multi_workspace(size_t n) {
+  return align_up(16 + (size_t)red2_blocks(n) * sizeof(double), 256);
+}
+
+extern "C" int dincae_adam_step_multi(float* params, const float* grads, size_t grad_rank_stride, int world,
+                                      float* m, float* v, size_t n, float clip_norm, const float* lr,
+                                      float beta1, float beta2, float eps, float grad_scale, const double* denom,
+                                      const double* extra_sumsq, float* state,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!params || !grads || !m || !v || !lr || !state || !workspace || n == 0 || world <= 0) return DINCAE_EINVAL;
+  if (workspace_bytes < dincae_adam_multi_workspace(n)) return DINCAE_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = cuda_rc(cudaMemsetAsync(workspace, 0, 16, st));
+  if (rc) return rc;
+  launch_k(sumsq_multi_kernel, red2_blocks(n), 256, 0, st, grads, grad_rank_stride, world, n, grad_scale, denom,
+           extra_sumsq, clip_norm, lr, beta1, beta2, state, reinterpret_cast<RedWork2*>(workspace));
+  rc = check_launch();
+  if (rc) return rc;
+  size_t ub = (n + 255) / 256;
+  if (ub > 8 * 148) ub = 8 * 148;
+  launch_k(adam_multi_kernel, (unsigned)ub, 256, 0, st, params, grads, grad_rank_stride, world, m, v, n, grad_scale,
+           denom, beta1, beta2, eps, state);
+  return check_launch();
+}
+
+extern "C" int dincae_sum_ranks_f64(const double* in, size_t rank_stride, int world, int count, double* out,
+                                    void* stream) {
+  if (!in || !out || world <= 0 || count <= 0 || count > 32) return DINCAE_EINVAL;
+  launch_k(sum_ranks_f64_kernel, 1, 32, 0, (cudaStream_t)stream, in, rank_stride, world, count, out);
+  return check_launch();
+}

@@ -191,7 +191,10 @@ class Plan:
 class Network:
     """Buffers + kernel sequences for one Plan on the current CUDA device."""
 
-    def __init__(self, plan, max_batch, train=True, device=None):
+    def __init__(self, plan, max_batch, train=True, device=None, factored=False, world=1, rank=0):
+        """``factored``: keep the weight gradients of the dense bottleneck as their factors (layer
+        input x, pre-activation gradient dz) instead of materialising x^T dz (csrc/dense_factored.cu);
+        ``world`` / ``rank``: data-parallel layout of the per-rank gradient blob (see _setup_factored)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.DincaeError("dincae_b200 needs a CUDA device (no CPU fallback)")
@@ -201,10 +204,11 @@ class Network:
         self.dev = torch.device(device if device is not None else "cuda")
         P, B, dev = plan, self.Bmax, self.dev
         f32 = dict(dtype=torch.float32, device=dev)
+        self._setup_factored(factored, world, rank)
 
         self.params = torch.zeros(P.n_params_flat, **f32)
         if train:
-            self.grads = torch.zeros(P.n_params_flat, **f32)
+            self.grads = None if self.factored else torch.zeros(P.n_params_flat, **f32)
             self.adam_m = torch.zeros(P.n_params_flat, **f32)
             self.adam_v = torch.zeros(P.n_params_flat, **f32)
             self.adam_state = torch.zeros(8, **f32)
@@ -217,9 +221,13 @@ class Network:
         self.xtrue = torch.zeros(B, P.H, P.W, 2, **f32)
         self.n_noncloud = torch.zeros(1, dtype=torch.int32, device=dev)
         nd = len(P.dense_units)
+        if self.factored:
+            # the bottleneck activations that are gradient factors live in the per-rank blob
+            self.X[P.L] = self.Fx[0].view(B, P.ep[P.L], P.sizes[P.L][0], P.sizes[P.L][1], 4)
         self.F = [self.X[P.L].view(B, -1)]
         for i in range(nd):
-            self.F.append(torch.zeros(B, P.dense_pad[i + 1], **f32))
+            last = i == nd - 1
+            self.F.append(self.Fx[i + 1] if (self.factored and not last) else torch.zeros(B, P.dense_pad[i + 1], **f32))
         self.D = [self.F[-1].view(B, P.ep[P.L], P.sizes[P.L][0], P.sizes[P.L][1], 4)]
         for l in range(1, P.L + 1):
             h, w = P.sizes[P.L - l]
@@ -234,13 +242,16 @@ class Network:
                 torch.zeros(B, P.ep[l], P.sizes[l - 1][0], (P.sizes[l - 1][1] + 3) // 4,
                             dtype=torch.int16, device=dev) for l in range(1, P.L + 1)]
             self.GD = [torch.zeros_like(d) for d in self.D]           # dZ of decoder convs / dense out
+            if self.factored:
+                self.GD[0] = self.dZf[nd].view(self.D[0].shape)
             self.dX = [None] + [torch.zeros_like(self.X[k]) for k in range(1, P.L + 1)]
             self.dXskip = [None] * (P.L + 1)
             for l in range(1, P.L + 1):
                 _, sk, r = P.dec_sources(l)
                 if sk and r >= 1:
                     self.dXskip[r] = torch.zeros_like(self.X[r])
-            self.dZ = [None] + [torch.zeros_like(self.F[i + 1]) for i in range(nd)]
+            self.dZ = [None] + [self.dZf[i + 1] if self.factored else torch.zeros_like(self.F[i + 1])
+                                for i in range(nd)]
             if nd:
                 self.dZ[nd] = self.GD[0].view(B, -1)
             self.loss_sums = torch.zeros(4, dtype=torch.float64, device=dev)
@@ -248,6 +259,7 @@ class Network:
             self.l2_out = torch.zeros(1, **f32)
             ws.append(self.lib.dincae_head_loss_workspace(B, P.H, P.W))
             ws.append(self.lib.dincae_adam_workspace(P.n_params_flat))
+            ws += self._factored_workspaces()
             for e in P.entries:
                 if e["kind"] == "conv_w":
                     h, w = self._conv_res(e)
@@ -262,6 +274,77 @@ class Network:
         self._ent = {e["name"]: e for e in P.entries}
         self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
         self.tracer = None       # optional callable(label, fn, args, alg_bytes, alg_flops)
+
+    # ---- factored dense gradients / per-rank gradient blob ---------------------------------------
+    def _setup_factored(self, factored, world, rank):
+        """Factored mode: everything a rank contributes to the optimiser step sits in ONE
+        contiguous per-rank blob of floats,
+            [x_0 | dz_1 | x_1 | dz_2 | ... | gradients of all other parameters | 4 loss sums (f64)],
+        so that data-parallel ranks exchange it with a single all-gather into ``blob_all``
+        [world][blob_len]; the optimiser kernels read all ranks' blobs in place, in rank order."""
+        P, B = self.plan, self.Bmax
+        nd = len(P.dense_units)
+        self.factored = bool(factored) and nd > 0 and self.train
+        self.world, self.rank = int(world), int(rank)
+        self.n_dense = 0
+        if not self.factored:
+            return
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        ents = [e for e in P.entries if e["kind"] == "dense_w"]
+        assert ents[0]["offset"] == 0, "dense kernels are expected at the start of the flat buffer"
+        self.n_dense = layout.round_up(ents[-1]["offset"] + ents[-1]["size"], 64)
+        self.n_rest = P.n_params_flat - self.n_dense
+        off = 0
+        self._fact = []
+        for i in range(nd):
+            kx, kz = P.dense_pad[i], P.dense_pad[i + 1]
+            self._fact.append(dict(x=off, z=off + layout.round_up(B * kx, 64), K=kx, N=kz))
+            off = self._fact[-1]["z"] + layout.round_up(B * kz, 64)
+        self._rest_off = off
+        off += layout.round_up(self.n_rest, 64)
+        self._loss_off = off
+        off += 64
+        self.blob_len = off
+        self.blob_all = torch.zeros(self.world, off, **f32)
+        self.blob = self.blob_all[self.rank]
+        self.Fx = [self.blob[f["x"]: f["x"] + B * f["K"]].view(B, f["K"]) for f in self._fact]
+        self.dZf = [None] + [self.blob[f["z"]: f["z"] + B * f["N"]].view(B, f["N"]) for f in self._fact]
+        self.grads_rest = self.blob[self._rest_off: self._rest_off + self.n_rest]
+        self.loss_sums_local = self.blob[self._loss_off: self._loss_off + 8].view(torch.float64)
+        self.extra_sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+
+    def _factored_workspaces(self):
+        if not self.factored:
+            return []
+        return [self.lib.dincae_dense_factored_workspace(self.world * self.Bmax, f["K"], f["N"]) for f in self._fact] + \
+            [self.lib.dincae_adam_multi_workspace(self.n_rest)]
+
+    def _g(self, name):
+        """Gradient slice of variable ``name`` (in the per-rank blob when factored)."""
+        e = self._ent[name]
+        if self.factored:
+            o = e["offset"] - self.n_dense
+            assert o >= 0, "dense kernels have no materialised gradient in factored mode"
+            return self.grads_rest[o: o + e["size"]]
+        return self.grads[e["offset"]: e["offset"] + e["size"]]
+
+    def _loss_sums_dst(self):
+        return self.loss_sums_local if self.factored else self.loss_sums
+
+    def _dense_weight_grad(self, i, B, part=2):
+        """Weight + bias gradient of dense layer i -- or, factored, only the bias gradient."""
+        P = self.plan
+        name = "dense" if i == 0 else "dense_%d" % i
+        K, N = P.dense_pad[i], P.dense_pad[i + 1]
+        kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+        if self.factored:
+            self._call("dense_bias_grad(%d)" % i, "dincae_dense_bias_grad", (
+                ptr(self.dZ[i + 1]), B, N, N, ptr(self._g(name + "/bias")), stream_ptr()), 4 * (B * nn + nn), 0)
+            return
+        self._fork(lambda: self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
+            ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
+            ptr(self._g(name + "/kernel")), ptr(self._g(name + "/bias")),
+            stream_ptr()), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn), part)
 
     def _fork(self, fn, part=1):
         """Run ``fn`` (which enqueues kernels) on the side stream, after everything enqueued so
@@ -306,8 +389,24 @@ class Network:
     def get_params_tf(self):
         return self.plan.unpack(self.params.cpu().numpy())
 
-    def get_grads_tf(self):
-        return self.plan.unpack(self.grads.cpu().numpy())
+    def flat_grads(self, B=None):
+        """Flat gradient vector (a copy).  Factored mode: the dense kernels' gradients are expanded
+        from their factors and the other gradients summed over the ranks' blobs."""
+        if not self.factored:
+            return self.grads.clone()
+        B = self.Bmax if B is None else B
+        flat = torch.zeros(self.plan.n_params_flat, dtype=torch.float32, device=self.dev)
+        flat[self.n_dense:] = self.blob_all[:, self._rest_off: self._rest_off + self.n_rest].sum(dim=0)
+        ba = self.blob_all
+        for i, f in enumerate(self._fact):
+            e = self._ent[("dense" if i == 0 else "dense_%d" % i) + "/kernel"]
+            check(self.lib.dincae_dense_factored_expand(
+                ba.data_ptr() + 4 * f["x"], self.blob_len, f["K"], ba.data_ptr() + 4 * f["z"], self.blob_len, f["N"],
+                self.world, B, f["K"], f["N"], flat.data_ptr() + 4 * e["offset"], f["N"], stream_ptr()), "expand")
+        return flat
+
+    def get_grads_tf(self, B=None):
+        return self.plan.unpack(self.flat_grads(B).cpu().numpy())
 
     def _w(self, name, buf=None):
         e = self._ent[name]
@@ -397,7 +496,7 @@ class Network:
             return self._backward_encoder(B, has_dense, wss, wsn, st)
         self._call("head_loss", "dincae_head_loss", (
             ptr(self.D[L]), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
-            ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self.loss_sums),
+            ptr(self.n_noncloud) if normalise else None, ptr(self.GD[L]), ptr(self._loss_sums_dst()),
             ptr(self.loss_out), wsp, wsn, st), 24 * B * P.H * P.W, 0)
         has_dense = len(P.dense_units) > 0
         for l in range(L, 0, -1):
@@ -413,7 +512,7 @@ class Network:
             self._fork(lambda: self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.D[l - 1]), c0p, 1, ptr(self.X[r]) if sk else None, c1p,
                 ptr(self.GD[l]), None, None, NEG_SLOPE, P.dp[l], e["cout_pad"], B, h, w,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                ptr(self._g(name + "/kernel")), ptr(self._g(name + "/bias")),
                 wss, wsn, stream_ptr()), nb, 18 * (up + sk) * co * B * h * w), 1)
             prev_slope = NEG_SLOPE if l > 1 else (0.0 if has_dense else 1.0)
             want_skip = bool(sk) and r >= 1
@@ -430,10 +529,7 @@ class Network:
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
-            self._fork(lambda: self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
-                ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                stream_ptr()), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn), 2)
+            self._dense_weight_grad(i, B)
             dst = self.dZ[i] if i > 0 else self.dX[L].view(self.Bmax, -1)
             self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
                 ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
@@ -455,7 +551,7 @@ class Network:
             self._fork(lambda: self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad", (
                 ptr(self.X[l - 1]), P.ep[l - 1], 0, None, 0,
                 None, ptr(gpool), ptr(self.S[l]), NEG_SLOPE, P.ep[l], e["cout_pad"], B, h, w,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                ptr(self._g(name + "/kernel")), ptr(self._g(name + "/bias")),
                 wss, wsn, stream_ptr()), nb, 18 * ci * co * B * h * w), 4)
             if l > 1:
                 has_add = self.dXskip[l - 1] is not None
@@ -476,8 +572,13 @@ class Network:
             self.workspace.numel(), stream_ptr()), 4 * self.plan.n_params_tf, 0)
 
     def adam_step(self, clip_norm=5.0, l2_beta=0.0, beta1=0.9, beta2=0.999, eps=1e-8,
-                  grad_scale=1.0, denom=None):
-        """clip_by_global_norm + Adam on self.grads; learning rate read from self.lr."""
+                  grad_scale=1.0, denom=None, B=None):
+        """clip_by_global_norm + Adam on self.grads; learning rate read from self.lr.
+        Factored mode: ``B`` rows of every rank's factors are valid; the loss sums of all ranks
+        are reduced into ``self.loss_sums`` first (``denom`` usually points at its 4th entry)."""
+        if self.factored:
+            return self._adam_step_factored(clip_norm, l2_beta, beta1, beta2, eps, grad_scale, denom,
+                                            self.Bmax if B is None else B)
         self._call("adam_step", "dincae_adam_step", (
             ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
             self.plan.n_params_flat, self.plan.n_decay, l2_beta, clip_norm, ptr(self.lr),
@@ -485,11 +586,41 @@ class Network:
             ptr(self.workspace), self.workspace.numel(), stream_ptr()),
             28 * self.plan.n_params_tf, 0)
 
+    def _adam_step_factored(self, clip_norm, l2_beta, beta1, beta2, eps, grad_scale, denom, B):
+        if l2_beta != 0.0:
+            raise ValueError("the factored optimiser path has no L2 term (use factored=False)")
+        st = stream_ptr()
+        ba, L = self.blob_all, self.blob_len
+        base = ba.data_ptr()
+        self._call("sum_loss_sums", "dincae_sum_ranks_f64", (
+            base + 4 * self._loss_off, L // 2, self.world, 4, ptr(self.loss_sums), st), 32 * self.world, 0)
+        self.extra_sumsq.zero_()
+        wsp, wsn = ptr(self.workspace), self.workspace.numel()
+        for i, f in enumerate(self._fact):
+            self._call("dense_grad_sumsq(%d)" % i, "dincae_dense_factored_sumsq", (
+                base + 4 * f["x"], L, f["K"], base + 4 * f["z"], L, f["N"], self.world, B, f["K"], f["N"],
+                ptr(self.extra_sumsq), wsp, wsn, st), 4 * self.world * B * (f["K"] + f["N"]), 0)
+        nd_, nr = self.n_dense, self.n_rest
+        self._call("adam_step(conv + biases)", "dincae_adam_step_multi", (
+            ptr(self.params[nd_:]), base + 4 * self._rest_off, L, self.world, ptr(self.adam_m[nd_:]),
+            ptr(self.adam_v[nd_:]), nr, clip_norm, ptr(self.lr), beta1, beta2, eps, grad_scale, ptr(denom),
+            ptr(self.extra_sumsq), ptr(self.adam_state), wsp, wsn, st),
+            (24 + 8 * self.world) * nr, 0)
+        for i, f in enumerate(self._fact):
+            e = self._ent[("dense" if i == 0 else "dense_%d" % i) + "/kernel"]
+            o = e["offset"]
+            kk, nn = e["tf_shape"]
+            self._call("adam_dense_factored(%d)" % i, "dincae_adam_update_factored", (
+                ptr(self.params[o:]), ptr(self.adam_m[o:]), ptr(self.adam_v[o:]), f["N"],
+                base + 4 * f["x"], L, f["K"], base + 4 * f["z"], L, f["N"], self.world, B, f["K"], f["N"],
+                grad_scale, ptr(denom), beta1, beta2, eps, ptr(self.adam_state), st),
+                24 * kk * nn, 2 * self.world * B * kk * nn)
 
-def make_network(plan, max_batch, train=True, device=None):
+
+def make_network(plan, max_batch, train=True, device=None, **kw):
     """Network for ``plan``: planar-4 fp32 / TF32 kernels, or (``plan.lanes == 8``) the bf16 path."""
     cls = NetworkBF16 if plan.lanes == 8 else Network
-    return cls(plan, max_batch, train=train, device=device)
+    return cls(plan, max_batch, train=train, device=device, **kw)
 
 
 class NetworkBF16(Network):
@@ -499,7 +630,7 @@ class NetworkBF16(Network):
     the parameters, Adam state, the dense bottleneck, the network output and the loss stay fp32.
     The fp32 master kernels are converted to their bf16 operand copies once per step."""
 
-    def __init__(self, plan, max_batch, train=True, device=None):
+    def __init__(self, plan, max_batch, train=True, device=None, factored=False, world=1, rank=0):
         import os
         if plan.lanes != 8:
             raise ValueError("NetworkBF16 needs Plan(lanes=8)")
@@ -514,10 +645,11 @@ class NetworkBF16(Network):
         f32 = dict(dtype=torch.float32, device=dev)
         b16 = dict(dtype=torch.bfloat16, device=dev)
         L = P.L
+        self._setup_factored(factored, world, rank)
 
         self.params = torch.zeros(P.n_params_flat, **f32)
         if train:
-            self.grads = torch.zeros(P.n_params_flat, **f32)
+            self.grads = None if self.factored else torch.zeros(P.n_params_flat, **f32)
             self.adam_m = torch.zeros(P.n_params_flat, **f32)
             self.adam_v = torch.zeros(P.n_params_flat, **f32)
             self.adam_state = torch.zeros(8, **f32)
@@ -532,9 +664,10 @@ class NetworkBF16(Network):
         self.n_noncloud = torch.zeros(1, dtype=torch.int32, device=dev)
         nd = len(P.dense_units)
         hL, wL = P.sizes[L]
-        self.F = [torch.zeros(B, P.n_flat, **f32)] if nd else []
+        self.F = [self.Fx[0] if self.factored else torch.zeros(B, P.n_flat, **f32)] if nd else []
         for i in range(nd):
-            self.F.append(torch.zeros(B, P.dense_pad[i + 1], **f32))
+            last = i == nd - 1
+            self.F.append(self.Fx[i + 1] if (self.factored and not last) else torch.zeros(B, P.dense_pad[i + 1], **f32))
         self.D8 = [torch.zeros(B, P.ep8[L], hL, wL, 8, **b16) if nd else self.X8[L]]
         for l in range(1, L):
             h, w = P.sizes[L - l]
@@ -582,13 +715,15 @@ class NetworkBF16(Network):
                 _, sk, r = P.dec_sources(l)
                 if sk and r >= 1:
                     self.dXskip8[r] = torch.zeros_like(self.X8[r])
-            self.dZ = [None] + [torch.zeros_like(self.F[i + 1]) for i in range(nd)]
+            self.dZ = [None] + [self.dZf[i + 1] if self.factored else torch.zeros_like(self.F[i + 1])
+                                for i in range(nd)]
             self.dF0 = torch.zeros(B, P.n_flat, **f32) if nd else None
             self.loss_sums = torch.zeros(4, dtype=torch.float64, device=dev)
             self.loss_out = torch.zeros(2, **f32)
             self.l2_out = torch.zeros(1, **f32)
             ws.append(self.lib.dincae_head_loss_workspace(B, P.H, P.W))
             ws.append(self.lib.dincae_adam_workspace(P.n_params_flat))
+            ws += self._factored_workspaces()
             for e in P.entries:
                 if e["kind"] == "conv_w":
                     ws.append(self.lib.dincae_conv3x3_wgrad_bf16_workspace(e["cinp"], e["cout_pad"]))
@@ -712,7 +847,7 @@ class NetworkBF16(Network):
             return self._backward_encoder(B, wss, wsn, st)
         self._call("head_loss", "dincae_head_loss_bf16", (
             ptr(self.xrec), ptr(self.xtrue), B, P.H, P.W, int(bool(truth_uncertain)), NEG_SLOPE,
-            ptr(self.n_noncloud) if normalise else None, ptr(self.GD8[L]), ptr(self.loss_sums),
+            ptr(self.n_noncloud) if normalise else None, ptr(self.GD8[L]), ptr(self._loss_sums_dst()),
             ptr(self.loss_out), wsp, wsn, st), 40 * B * P.H * P.W, 0)
         for l in range(L, 0, -1):
             up, sk, r = P.dec_sources(l)
@@ -727,7 +862,7 @@ class NetworkBF16(Network):
             self._fork(lambda: self._call("conv3x3_wgrad(dec %d)" % l, "dincae_conv3x3_wgrad_bf16", (
                 ptr(self.D8[l - 1]), c0p8, 1, ptr(self.X8[r]) if sk else None, c1p8,
                 ptr(self.GD8[l]), None, None, NEG_SLOPE, P.dp8[l], e["cinp"], e["cout_pad"], B, h, w,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                ptr(self._g(name + "/kernel")), ptr(self._g(name + "/bias")),
                 wss, wsn, stream_ptr()), nb, 18 * (up + sk) * co * B * h * w), 1)
             prev_slope = NEG_SLOPE if l > 1 else (0.0 if nd else 1.0)
             prev_act = self.D8[l - 1] if (l > 1 or nd) else None
@@ -752,10 +887,7 @@ class NetworkBF16(Network):
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
-            self._fork(lambda: self._call("dense_bwd_weight(%d)" % i, "dincae_dense_bwd_weight", (
-                ptr(self.F[i]), ptr(self.dZ[i + 1]), B, K, N,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
-                stream_ptr()), 4 * (B * kk + B * nn + kk * nn), 2 * B * kk * nn), 2)
+            self._dense_weight_grad(i, B)
             dst = self.dZ[i] if i > 0 else self.dF0
             self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
                 ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
@@ -780,7 +912,7 @@ class NetworkBF16(Network):
             self._fork(lambda: self._call("conv3x3_wgrad(enc %d)" % l, "dincae_conv3x3_wgrad_bf16", (
                 ptr(self.X8[l - 1]), P.ep8[l - 1], 0, None, 0,
                 None, ptr(gpool), ptr(self.S8[l]), NEG_SLOPE, P.ep8[l], e["cinp"], e["cout_pad"], B, h, w,
-                ptr(self._w(name + "/kernel", self.grads)), ptr(self._w(name + "/bias", self.grads)),
+                ptr(self._g(name + "/kernel")), ptr(self._g(name + "/bias")),
                 wss, wsn, stream_ptr()), nb, 18 * ci * co * B * h * w), 4)
             if l > 1:
                 has_add = self.dXskip8[l - 1] is not None

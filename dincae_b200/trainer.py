@@ -28,8 +28,7 @@ class Trainer:
         self.l2_beta = float(l2_beta)
         self.noise_seed = int(noise_seed)
         self.jitter_std = jitter_std
-        self.net = make_network(plan, self.B, train=True, device=cube.dev)
-        self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
+        import os
         self.dist = None
         self.rank, self.world = 0, 1
         if dist_group is not None:
@@ -37,7 +36,17 @@ class Trainer:
             self.dist = dist
             self.group = dist_group if dist_group is not True else None
             self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-            dist.broadcast(self.net.params, src=0, group=self.group)
+        # Factored dense gradients (csrc/dense_factored.cu): default whenever there is a dense
+        # bottleneck and no L2 term.  Data parallel, the ranks then exchange ONE all-gather of
+        # their gradient blobs (factors + conv / bias gradients + loss sums) per step.
+        factored = (len(plan.dense_units) > 0 and self.l2_beta == 0.0 and self.world * self.B <= 1024
+                    and os.environ.get("DINCAE_FACTORED", "1") != "0")
+        self.net = make_network(plan, self.B, train=True, device=cube.dev, factored=factored,
+                                world=self.world, rank=self.rank)
+        self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
+        if self.dist is not None:
+            self.dist.broadcast(self.net.params, src=0, group=self.group)
+        self._nccl_in_graph = os.environ.get("DINCAE_NCCL_IN_GRAPH", "0") == "1"
         dev = cube.dev
         B = self.B
         # [frame(B) | cloud(B) | seq int64 (2B int32)]
@@ -76,7 +85,7 @@ class Trainer:
 
     def _enqueue_update(self):
         net = self.net
-        net.adam_step(clip_norm=self.clip_grad, l2_beta=self.l2_beta, denom=net.loss_sums[3:4])
+        net.adam_step(clip_norm=self.clip_grad, l2_beta=self.l2_beta, denom=net.loss_sums[3:4], B=self.B)
 
     def _run(self, key, fn):
         if not self.use_graph:
@@ -138,6 +147,18 @@ class Trainer:
         """One step on the indices already in ``self.idx_dev``."""
         if self.dist is None:
             self._run("step", lambda: (self._enqueue_fwd_bwd(), self._enqueue_update()))
+        elif self.net.factored:
+            # one exchange per step: every rank's blob (dense factors, the other gradients, loss
+            # sums) is all-gathered in place; the optimiser kernels then sum the ranks' copies in
+            # rank order, so all ranks apply bit-identical updates
+            net = self.net
+            gather = lambda: self.dist.all_gather_into_tensor(net.blob_all.view(-1), net.blob, group=self.group)
+            if self._nccl_in_graph:
+                self._run("step", lambda: (self._enqueue_fwd_bwd(), gather(), self._enqueue_update()))
+            else:
+                self._run("fwd_bwd", self._enqueue_fwd_bwd)
+                gather()
+                self._run("update", self._enqueue_update)
         else:
             # gradients become final in two phases; the big bucket (dense + decoder kernels)
             # is all-reduced on NCCL's stream while the encoder backward still runs

@@ -218,6 +218,50 @@ int dincae_dense_bwd_data(const float* dz, const float* w, const float* act_in,
 int dincae_dense_bwd_weight(const float* x, const float* dz, int B, int K, int N,
                             float* dw, float* db, void* stream);
 
+/* ---- dense-bottleneck gradients in factored form (new capability) ------------------------------
+ * The gradient of a dense kernel is dW = x^T dz (x [Bt,K]: the layer input, dz [Bt,N]: gradient of
+ * its pre-activation, Bt frames of the GLOBAL batch).  These entry points let the optimiser work
+ * from the factors instead of a materialised dW (DINCAE/__init__.py:479-483 MatMul gradients,
+ * :598-603 clip_by_global_norm + ApplyAdam): no dW write / re-reads, and data-parallel ranks
+ * all-gather Bt x (K + N) floats instead of all-reducing K x N.
+ * Factor rows are addressed as `world` per-rank blocks: row bt lives at
+ *   base + (bt / rows_per_rank) * rank_stride + (bt % rows_per_rank) * ld      (floats),
+ * i.e. an all-gathered buffer of per-rank blobs is used in place (world = 1: a plain matrix).
+ *   dense_factored_sumsq : *sumsq += ||x^T dz||_F^2 = sum_{b,b'} (x_b.x_b')(dz_b.dz_b') (fixed order).
+ *   adam_update_factored : TF-Adam on w [K][ldw] (N columns) with g = x^T dz * grad_scale / *denom *
+ *                          state[4] (clip scale), lr_t = state[3] -- the scalars adam_step_multi left.
+ *   dense_factored_expand: dw [K][ldw] = x^T dz (tests / callers that want the matrix).
+ *   dense_bias_grad      : db[n] = sum_b dz[b][n] over the B rows (row pitch ld) of one rank.
+ *   adam_step_multi      : global norm + TF-Adam over n parameters whose gradient is given as `world`
+ *                          copies (summed on the fly in rank order), plus *extra_sumsq (device double,
+ *                          may be NULL) = sum of squares of the factored gradients; writes state[] like
+ *                          dincae_adam_step.  No L2 term on this path.
+ *   sum_ranks_f64        : out[k] = sum_r in[r * rank_stride + k] (doubles; the per-rank loss sums). */
+size_t dincae_dense_factored_workspace(int Bt, int K, int N);
+int dincae_dense_factored_sumsq(const float* x, size_t x_rank_stride, int ldx,
+                                const float* dz, size_t dz_rank_stride, int lddz,
+                                int world, int rows_per_rank, int K, int N, double* sumsq,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int dincae_adam_update_factored(float* w, float* m, float* v, int ldw,
+                                const float* x, size_t x_rank_stride, int ldx,
+                                const float* dz, size_t dz_rank_stride, int lddz,
+                                int world, int rows_per_rank, int K, int N,
+                                float grad_scale, const double* denom, float beta1, float beta2,
+                                float eps, const float* state, void* stream);
+int dincae_dense_factored_expand(const float* x, size_t x_rank_stride, int ldx,
+                                 const float* dz, size_t dz_rank_stride, int lddz,
+                                 int world, int rows_per_rank, int K, int N, float* dw, int ldw,
+                                 void* stream);
+int dincae_dense_bias_grad(const float* dz, int B, int N, int ld, float* db, void* stream);
+size_t dincae_adam_multi_workspace(size_t n);
+int dincae_adam_step_multi(float* params, const float* grads, size_t grad_rank_stride, int world,
+                           float* m, float* v, size_t n, float clip_norm, const float* lr,
+                           float beta1, float beta2, float eps, float grad_scale, const double* denom,
+                           const double* extra_sumsq, float* state,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int dincae_sum_ranks_f64(const double* in, size_t rank_stride, int world, int count, double* out,
+                         void* stream);
+
 /* ---- output head, loss ------------------------------------------------------------- */
 
 /* DINCAE/__init__.py:520-523 + sinv :298-299: xrec P4 [B][1][H][W][4] (lanes 0,1) ->
