@@ -33,6 +33,19 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 METRIC = "train frames/sec at 112x112 (value) & 512x512 (config_d); recon frames/sec alongside"
 UNIT = "frames/s"
 
@@ -236,7 +249,7 @@ def run_reference(a):
             "model_only_fps": res["model_only_fps"],
             "note": "TF 1.15 (setup.py:19) is not installable here; this arm times the oracle "
                     "restatement of the reference's CPU path (kind=port)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def peak_bf16():
@@ -665,13 +678,19 @@ def run_ours(a):
         except Exception as e:            # noqa: BLE001
             line["config_d"] = {"error": repr(e)[:300]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version
+    # banner, prints of the reference-facing API) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

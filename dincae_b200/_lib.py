@@ -69,6 +69,8 @@ SIGNATURES = {
     "dincae_adam_step_multi": (c_int, [vp, vp, c_size_t, c_int, vp, vp, c_size_t, c_float, vp, c_float, c_float,
                                        c_float, c_float, vp, vp, vp, vp, c_size_t, vp]),
     "dincae_sum_ranks_f64": (c_int, [vp, c_size_t, c_int, c_int, vp, vp]),
+    "dincae_f64_to_hilo": (c_int, [vp, c_int, vp, vp]),
+    "dincae_hilo_to_f64": (c_int, [vp, c_int, vp, vp]),
     "dincae_head_recon": (c_int, [vp, c_int, c_int, c_int, vp, vp, vp]),
     "dincae_head_recon_records": (c_int, [vp, c_int, c_int, c_int, vp, vp, c_float, c_int, c_int, vp, vp]),
     "dincae_head_loss_workspace": (c_size_t, [c_int, c_int, c_int]),

@@ -93,27 +93,63 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(Factor fx, Factor fz,
 }
 
 // sumsq[0] += sum over pairs of Gx[pair] * Gz[pair], the Gram entries summed over the chunk
-// partials in a fixed order (one CTA; deterministic).
-__global__ void __launch_bounds__(1024) gram_finish_kernel(const float* __restrict__ partial, int chunks_x,
-                                                           int chunks_z, int chunks_stride, int npairs,
-                                                           double* __restrict__ sumsq) {
+// partials.  One thread per pair (its chunk loads are independent and all in flight -- a single
+// CTA walking the chunks one dependent load after the other took 75 us at config A), fixed-order
+// block sums, and the last CTA adds the block sums in block order: deterministic.
+struct GramWork {
+  unsigned int counter;
+  unsigned int pad[3];
+  double block_sum[1];
+};
+
+__global__ void __launch_bounds__(256) gram_finish_kernel(const float* __restrict__ partial, int chunks_x,
+                                                          int chunks_z, int chunks_stride, int npairs,
+                                                          double* __restrict__ sumsq, GramWork* __restrict__ work) {
   pdl_trigger();
   pdl_wait();
-  double mine = 0.0;
-  for (int pr = threadIdx.x; pr < npairs; pr += blockDim.x) {
+  const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+  double prod = 0.0;
+  if (pr < npairs) {
+    float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f, gx3 = 0.f, gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gz3 = 0.f;
     double gx = 0.0, gz = 0.0;
-    for (int c = 0; c < chunks_x; ++c) gx += (double)partial[(size_t)c * npairs + pr];
-    for (int c = 0; c < chunks_z; ++c) gz += (double)partial[((size_t)chunks_stride + c) * npairs + pr];
-    mine += gx * gz;
+    const float* px = partial + pr;
+    const float* pz = partial + (size_t)chunks_stride * npairs + pr;
+    int c = 0;
+    for (; c + 4 <= chunks_x; c += 4) {
+      gx0 = __ldg(px + (size_t)c * npairs); gx1 = __ldg(px + (size_t)(c + 1) * npairs);
+      gx2 = __ldg(px + (size_t)(c + 2) * npairs); gx3 = __ldg(px + (size_t)(c + 3) * npairs);
+      gx += ((double)gx0 + (double)gx1) + ((double)gx2 + (double)gx3);
+    }
+    for (; c < chunks_x; ++c) gx += (double)__ldg(px + (size_t)c * npairs);
+    c = 0;
+    for (; c + 4 <= chunks_z; c += 4) {
+      gz0 = __ldg(pz + (size_t)c * npairs); gz1 = __ldg(pz + (size_t)(c + 1) * npairs);
+      gz2 = __ldg(pz + (size_t)(c + 2) * npairs); gz3 = __ldg(pz + (size_t)(c + 3) * npairs);
+      gz += ((double)gz0 + (double)gz1) + ((double)gz2 + (double)gz3);
+    }
+    for (; c < chunks_z; ++c) gz += (double)__ldg(pz + (size_t)c * npairs);
+    prod = gx * gz;
   }
-  mine = warp_sum(mine);
-  __shared__ double red[32];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+  prod = warp_sum(prod);
+  __shared__ double red[8];
+  __shared__ bool is_last;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = prod;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    for (int w = 0; w < 8; ++w) t += red[w];
+    work->block_sum[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(&work->counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += *((volatile double*)&work->block_sum[k]);
     sumsq[0] += t;
+    work->counter = 0;
   }
 }
 
@@ -342,9 +378,31 @@ __global__ void sum_ranks_f64_kernel(const double* __restrict__ in, size_t rank_
   out[k] = s;
 }
 
+// doubles <-> (hi, lo) float pairs, so that a float32 all-reduce can carry the loss sums exactly
+// enough (the pair sums recombine to ~1e-14 relative): out[2k] = float(x), out[2k+1] = float(x - hi)
+__global__ void f64_to_hilo_kernel(const double* __restrict__ in, int count, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = threadIdx.x;
+  if (k >= count) return;
+  const double x = in[k];
+  const float hi = (float)x;
+  out[2 * k] = hi;
+  out[2 * k + 1] = (float)(x - (double)hi);
+}
+__global__ void hilo_to_f64_kernel(const float* __restrict__ in, int count, double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = threadIdx.x;
+  if (k >= count) return;
+  out[k] = (double)in[2 * k] + (double)in[2 * k + 1];
+}
+
 }  // namespace dincae
 
 using namespace dincae;
+
+static size_t gram_work_bytes(int Bt) { return align_up(16 + (size_t)((Bt * Bt + 255) / 256) * sizeof(double), 256); }
 
 static int gram_chunks(int ncols, int Bt, int* cols_per_cta) {
   // about two CTAs per SM over (column chunks x pair tiles); chunks are multiples of GR_COLS columns
@@ -363,7 +421,7 @@ extern "C" size_t dincae_dense_factored_workspace(int Bt, int K, int N) {
   int per;
   const int wide = K > N ? K : N;
   const int chunks = gram_chunks(wide, Bt, &per);
-  return align_up((size_t)2 * chunks * Bt * Bt * sizeof(float), 256);
+  return align_up((size_t)2 * chunks * Bt * Bt * sizeof(float), 256) + gram_work_bytes(Bt);
 }
 
 extern "C" int dincae_dense_factored_sumsq(const float* x, size_t x_rank_stride, int ldx,
@@ -385,8 +443,14 @@ extern "C" int dincae_dense_factored_sumsq(const float* x, size_t x_rank_stride,
            reinterpret_cast<float*>(workspace));
   int rc = check_launch();
   if (rc) return rc;
-  launch_k(gram_finish_kernel, 1, 1024, 0, st, reinterpret_cast<const float*>(workspace), chunks_x, chunks_z,
-           chunks, Bt * Bt, sumsq);
+  // the finish kernel's counter + block sums sit behind the partials; the counter is zero on entry
+  // (zeroed here once per call: cheap, and robust against an aborted earlier launch)
+  unsigned char* wk = reinterpret_cast<unsigned char*>(workspace) +
+                      align_up((size_t)2 * chunks * Bt * Bt * sizeof(float), 256);
+  rc = cuda_rc(cudaMemsetAsync(wk, 0, 16, st));
+  if (rc) return rc;
+  launch_k(gram_finish_kernel, (Bt * Bt + 255) / 256, 256, 0, st, reinterpret_cast<const float*>(workspace), chunks_x,
+           chunks_z, chunks, Bt * Bt, sumsq, reinterpret_cast<GramWork*>(wk));
   return check_launch();
 }
 
@@ -452,5 +516,17 @@ extern "C" int dincae_sum_ranks_f64(const double* in, size_t rank_stride, int wo
                                     void* stream) {
   if (!in || !out || world <= 0 || count <= 0 || count > 32) return DINCAE_EINVAL;
   launch_k(sum_ranks_f64_kernel, 1, 32, 0, (cudaStream_t)stream, in, rank_stride, world, count, out);
+  return check_launch();
+}
+
+extern "C" int dincae_f64_to_hilo(const double* in, int count, float* out, void* stream) {
+  if (!in || !out || count <= 0 || count > 32) return DINCAE_EINVAL;
+  launch_k(f64_to_hilo_kernel, 1, 32, 0, (cudaStream_t)stream, in, count, out);
+  return check_launch();
+}
+
+extern "C" int dincae_hilo_to_f64(const float* in, int count, double* out, void* stream) {
+  if (!in || !out || count <= 0 || count > 32) return DINCAE_EINVAL;
+  launch_k(hilo_to_f64_kernel, 1, 32, 0, (cudaStream_t)stream, in, count, out);
   return check_launch();
 }

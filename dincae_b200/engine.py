@@ -208,7 +208,9 @@ class Network:
 
         self.params = torch.zeros(P.n_params_flat, **f32)
         if train:
-            self.grads = None if self.factored else torch.zeros(P.n_params_flat, **f32)
+            # 64 extra floats: tail that carries the loss sums through the gradient all-reduce
+            self.grads_ext = None if self.factored else torch.zeros(P.n_params_flat + 64, **f32)
+            self.grads = None if self.factored else self.grads_ext[:P.n_params_flat]
             self.adam_m = torch.zeros(P.n_params_flat, **f32)
             self.adam_v = torch.zeros(P.n_params_flat, **f32)
             self.adam_state = torch.zeros(8, **f32)
@@ -330,6 +332,18 @@ class Network:
 
     def _loss_sums_dst(self):
         return self.loss_sums_local if self.factored else self.loss_sums
+
+    def pack_loss_sums(self):
+        """Loss sums -> (hi, lo) float pairs in the tail of the gradient buffer (materialised path,
+        data parallel: ONE float32 all-reduce of ``grads_ext`` carries gradients and loss sums)."""
+        n = self.plan.n_params_flat
+        self._call("pack_loss_sums", "dincae_f64_to_hilo", (
+            ptr(self.loss_sums), 4, ptr(self.grads_ext[n:]), stream_ptr()), 64, 0)
+
+    def unpack_loss_sums(self):
+        n = self.plan.n_params_flat
+        self._call("unpack_loss_sums", "dincae_hilo_to_f64", (
+            ptr(self.grads_ext[n:]), 4, ptr(self.loss_sums), stream_ptr()), 64, 0)
 
     def _dense_weight_grad(self, i, B, part=2):
         """Weight + bias gradient of dense layer i -- or, factored, only the bias gradient."""
@@ -649,7 +663,8 @@ class NetworkBF16(Network):
 
         self.params = torch.zeros(P.n_params_flat, **f32)
         if train:
-            self.grads = None if self.factored else torch.zeros(P.n_params_flat, **f32)
+            self.grads_ext = None if self.factored else torch.zeros(P.n_params_flat + 64, **f32)
+            self.grads = None if self.factored else self.grads_ext[:P.n_params_flat]
             self.adam_m = torch.zeros(P.n_params_flat, **f32)
             self.adam_v = torch.zeros(P.n_params_flat, **f32)
             self.adam_state = torch.zeros(8, **f32)

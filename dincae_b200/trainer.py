@@ -11,6 +11,8 @@ are left un-normalised, summed with an NCCL all-reduce, and divided by the globa
 observed pixels inside the Adam kernel, so N ranks x B frames is numerically a single
 batch of N*B.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -39,14 +41,21 @@ class Trainer:
         # Factored dense gradients (csrc/dense_factored.cu): default whenever there is a dense
         # bottleneck and no L2 term.  Data parallel, the ranks then exchange ONE all-gather of
         # their gradient blobs (factors + conv / bias gradients + loss sums) per step.
+        n_dense = sum(e["size"] for e in plan.entries if e["kind"] == "dense_w")
+        want = os.environ.get("DINCAE_FACTORED", "auto")
+        # worth it when the dense kernels are big enough for their gradient traffic to matter
+        # (configs[3]: 688 M parameters, 2.75 GB to all-reduce otherwise); at config A (2.8 M) the
+        # step is latency-bound and the materialised path is a dozen small launches shorter
+        # (measured on 2 GPUs: 0.872 ms factored vs the single all-reduce below)
+        auto = n_dense >= 32 * 1024 * 1024
         factored = (len(plan.dense_units) > 0 and self.l2_beta == 0.0 and self.world * self.B <= 1024
-                    and os.environ.get("DINCAE_FACTORED", "1") != "0")
+                    and (want == "1" or (want == "auto" and auto)))
         self.net = make_network(plan, self.B, train=True, device=cube.dev, factored=factored,
                                 world=self.world, rank=self.rank)
         self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
         if self.dist is not None:
             self.dist.broadcast(self.net.params, src=0, group=self.group)
-        self._nccl_in_graph = os.environ.get("DINCAE_NCCL_IN_GRAPH", "0") == "1"
+        self._nccl_in_graph = os.environ.get("DINCAE_NCCL_IN_GRAPH", "1") == "1"
         dev = cube.dev
         B = self.B
         # [frame(B) | cloud(B) | seq int64 (2B int32)]
@@ -64,6 +73,7 @@ class Trainer:
         self._ring = torch.zeros(1024, 4, dtype=torch.float64).pin_memory()
         self._ring_l2 = torch.zeros(1024, 1, dtype=torch.float32).pin_memory()
         self._pending = []          # ring slots not yet converted to floats
+        self._stash = []            # entries drained because the ring filled up between two flushes
         self._ring_pos = 0
         self.step_count = 0
         self.launches_per_step = None
@@ -160,23 +170,43 @@ class Trainer:
                 gather()
                 self._run("update", self._enqueue_update)
         else:
-            # gradients become final in two phases; the big bucket (dense + decoder kernels)
-            # is all-reduced on NCCL's stream while the encoder backward still runs
-            big, rest = self.net.grad_buckets()
-            g = self.net.grads
-            self._run("fwd_bwd1", lambda: self._enqueue_fwd_bwd((1,)))
-            h_big = self.dist.all_reduce(g[big[0]:big[1]], group=self.group, async_op=True)
-            self._run("bwd2", lambda: self._enqueue_fwd_bwd((2,)))
-            hs = [self.dist.all_reduce(g[rest[0]:rest[1]], group=self.group, async_op=True),
-                  self.dist.all_reduce(self.net.loss_sums, group=self.group, async_op=True)]
-            h_big.wait()
-            for h in hs:
-                h.wait()
-            self._run("update", self._enqueue_update)
+            # materialised gradients: ONE all-reduce of [all gradients | loss sums as (hi, lo) float
+            # pairs] after the backward pass (round 1 issued three collectives with host-side waits
+            # in between, pure latency at 11.5 MB), captured with the kernels into one graph when
+            # NCCL capture is enabled
+            net = self.net
+            n_all = net.plan.n_params_flat + 8
+            (b0, b1), _ = net.grad_buckets()
+            split = os.environ.get("DINCAE_DP_BUCKETS", "2") == "2" and b1 < n_all
+
+            def fwd_bwd_reduce():
+                # the big bucket (dense + decoder kernels, 97 % of the bytes) is final after phase 1:
+                # its all-reduce runs next to the encoder backward; the rest (encoder kernels, biases,
+                # loss sums) follows as one small collective
+                if split:
+                    self._enqueue_fwd_bwd((1,))
+                    h = self.dist.all_reduce(net.grads_ext[b0:b1], group=self.group, async_op=True)
+                    self._enqueue_fwd_bwd((2,))
+                    net.pack_loss_sums()
+                    self.dist.all_reduce(net.grads_ext[b1:n_all], group=self.group)
+                    h.wait()
+                else:
+                    self._enqueue_fwd_bwd()
+                    net.pack_loss_sums()
+                    self.dist.all_reduce(net.grads_ext[:n_all], group=self.group)
+
+            if self._nccl_in_graph:
+                self._run("step", lambda: (fwd_bwd_reduce(), net.unpack_loss_sums(), self._enqueue_update()))
+            else:
+                self._run("fwd_bwd", lambda: (self._enqueue_fwd_bwd(), net.pack_loss_sums()))
+                self.dist.all_reduce(net.grads_ext[:n_all], group=self.group)
+                self._run("update", lambda: (net.unpack_loss_sums(), self._enqueue_update()))
         # loss bookkeeping: 4 sums + L2 value -> pinned ring (async)
         slot = self._ring_pos % self._ring.shape[0]
         if len(self._pending) >= self._ring.shape[0] - 1:
-            self.flush_losses()
+            # ring full in the middle of an epoch: keep the drained entries for the next
+            # flush_losses() of the caller instead of dropping them
+            self._stash += self._drain()
         self._ring[slot].copy_(self.net.loss_sums, non_blocking=True)
         if self.l2_beta != 0.0:
             self._ring_l2[slot].copy_(self.net.l2_out, non_blocking=True)
@@ -186,6 +216,11 @@ class Trainer:
 
     def flush_losses(self):
         """Synchronise and return [(cost, RMS), ...] of the steps since the last flush."""
+        out = self._stash + self._drain()
+        self._stash = []
+        return out
+
+    def _drain(self):
         if not self._pending:
             return []
         torch.cuda.current_stream().synchronize()

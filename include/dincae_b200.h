@@ -261,6 +261,10 @@ int dincae_adam_step_multi(float* params, const float* grads, size_t grad_rank_s
                            void* workspace, size_t workspace_bytes, void* stream);
 int dincae_sum_ranks_f64(const double* in, size_t rank_stride, int world, int count, double* out,
                          void* stream);
+/* count (<= 32) doubles <-> (hi, lo) float pairs: lets ONE float32 all-reduce carry the gradient
+ * buffer and, in its tail, the loss sums (pair sums recombine to ~1e-14 relative). */
+int dincae_f64_to_hilo(const double* in, int count, float* out, void* stream);
+int dincae_hilo_to_f64(const float* in, int count, double* out, void* stream);
 
 /* ---- output head, loss ------------------------------------------------------------- */
 

@@ -1,0 +1,91 @@
+"""Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py [A|D]
+N ranks x B frames through Trainer(dist_group=True) must equal one rank with N*B frames after a few
+optimisation steps (same global index stream, same noise keys).  Every rank also runs the
+single-process reference itself, so no extra launch is needed.  Rank 0 prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dincae_b200 import synthetic  # noqa: E402
+from dincae_b200.data import DeviceCube  # noqa: E402
+from dincae_b200.engine import Plan  # noqa: E402
+from dincae_b200.sampler import TrainSampler  # noqa: E402
+from dincae_b200.trainer import Trainer  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "A"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+
+if cfg == "A":
+    T, H, W, B, filt, skip, lanes, nf = 120, 112, 112, 50, (16, 24, 36, 54), (1, 2, 3, 4), 4, 1
+else:
+    T, H, W, B, filt, skip, lanes, nf = 40, 512, 512, 4, (32, 48, 72, 108, 162), (1, 2, 3, 4, 5), 8, 4
+fields, missing = [], []
+for k, kind in enumerate(["sst", "chl", "wind", "wind"][:nf]):
+    lon, lat, time_, data, mask = synthetic.sst_like_cube(T=T, H=H, W=W, seed=100 + k, kind=kind)
+    fields.append(data)
+    missing.append(np.ma.getmaskarray(data))
+cube = DeviceCube(lon, lat, time_, fields, missing, [1.0] * nf, 3)
+plan = Plan(H, W, cube.nvar, filt, (0.2,), skip, lanes=lanes)
+jit = [0.05] * nf
+out = {"config": cfg, "world": world, "frames_per_rank": B, "steps": steps,
+       "nccl_in_graph": os.environ.get("DINCAE_NCCL_IN_GRAPH", "1"), "dp_buckets": os.environ.get("DINCAE_DP_BUCKETS", "2")}
+
+dp = Trainer(plan, cube, B, noise_seed=11, jitter_std=jit, dist_group=True, init_seed=5)
+dp.set_lr(1e-3)
+out["factored"] = bool(dp.net.factored)
+import random
+random.seed(3)
+sampler = TrainSampler(T, B * world, 45, seed=7)
+batches = [sampler.next_batch() for _ in range(steps)]
+for f, c, q in batches:
+    s = slice(rank * B, (rank + 1) * B)
+    dp.train_step(f[s], c[s], q[s])
+dp_losses = dp.flush_losses()
+p_dp = dp.net.params.clone()
+# timing of the data-parallel step (graphs captured by now)
+dist.barrier()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20):
+    dp.run_step()
+torch.cuda.synchronize()
+out["dp_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / 20
+# all ranks hold identical parameters
+mine = dp.net.params.double().sum().reshape(1)
+allsums = [torch.zeros_like(mine) for _ in range(world)]
+dist.all_gather(allsums, mine)
+out["ranks_identical"] = bool(all(torch.equal(a, allsums[0]) for a in allsums))
+del dp
+torch.cuda.empty_cache()
+
+ref = Trainer(plan, cube, B * world, noise_seed=11, jitter_std=jit, dist_group=None, init_seed=5)
+ref.set_lr(1e-3)
+for f, c, q in batches:
+    ref.train_step(f, c, q)
+ref_losses = ref.flush_losses()
+p_ref = ref.net.params
+d = (p_dp - p_ref).abs()
+out["max_abs_param_diff"] = float(d.max())
+out["mean_abs_param_diff"] = float(d.mean())
+out["max_rel_loss_diff"] = float(max(abs(a[0] - b[0]) / max(abs(b[0]), 1e-9) for a, b in zip(dp_losses, ref_losses)))
+out["losses_dp"] = [a[0] for a in dp_losses]
+out["losses_single"] = [a[0] for a in ref_losses]
+# fp32/TF32: summation order only; bf16: the order also moves bf16 roundings of the next step
+tol = 1e-5 if lanes == 4 else 1e-4
+out["tolerance_rel_loss"] = tol
+out["pass"] = bool(out["max_rel_loss_diff"] < tol and out["mean_abs_param_diff"] < 2e-6 and out["ranks_identical"])
+if rank == 0:
+    print(json.dumps(out), flush=True)
+dist.barrier()
+dist.destroy_process_group()
