@@ -56,6 +56,11 @@ SIGNATURES = {
     "dincae_dense_fwd": (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_data": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
     "dincae_dense_bwd_weight": (c_int, [vp, vp, c_int, c_int, c_int, vp, vp, vp]),
+    "dincae_dense_tc_weights_elems": (c_size_t, [c_int, c_int]),
+    "dincae_dense_tc_tile_weights": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+    "dincae_dense_tc_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "dincae_dense_tc_fwd": (c_int, [vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, c_int, vp, c_size_t, vp]),
+    "dincae_dense_tc_bwd_data": (c_int, [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, vp, c_size_t, vp]),
     "dincae_dense_factored_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_dense_factored_sumsq": (c_int, [vp, c_size_t, c_int, vp, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                             vp, vp, c_size_t, vp]),

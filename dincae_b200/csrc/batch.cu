@@ -323,6 +323,12 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   if (ndata == 1 && ntime_win == 3 && nvar_planes == 3)
     launch_k(build_batch_kernel<1, 3>, blocks, threads, 0, (cudaStream_t)stream, P);
+  else if (ndata == 4 && ntime_win == 3 && nvar_planes == 7)       // BASELINE configs[3]: SST, chl, u, v
+    launch_k(build_batch_kernel<4, 3>, blocks, threads, 0, (cudaStream_t)stream, P);
+  else if (ndata == 3 && ntime_win == 3 && nvar_planes == 6)
+    launch_k(build_batch_kernel<3, 3>, blocks, threads, 0, (cudaStream_t)stream, P);
+  else if (ndata == 2 && ntime_win == 3 && nvar_planes == 4)
+    launch_k(build_batch_kernel<2, 3>, blocks, threads, 0, (cudaStream_t)stream, P);
   else
     launch_k(build_batch_kernel<0, 0>, blocks, threads, 0, (cudaStream_t)stream, P);
   return check_launch();

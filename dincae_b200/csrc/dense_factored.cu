@@ -155,34 +155,52 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------
 // Adam update of a dense kernel w [K][ldw] (N columns used) from its gradient factors.
-// grid (ceil(N/256), ceil(K/32)); thread = 8 rows x 4 columns (the tiling of outer_kernel).
+// grid (ceil(N/256), ceil(K/16)); 256 threads; thread = 4 rows x 4 columns.  The thread's p, m, v
+// (12 float4) are requested BEFORE the factor loop, so their HBM latency hides behind the Bt FMAs
+// per weight; ~100 registers -> two CTAs per SM, one computing while the other streams.  (The
+// first version -- 8 rows per thread, loads after the FMAs, 193 registers, one CTA per SM -- ran
+// at 2.1-3.2 TB/s at configs[3].)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) adam_factored_kernel(float* __restrict__ w, float* __restrict__ m,
-                                                            float* __restrict__ v, int ldw, Factor fx, Factor fz,
-                                                            int Bt, int rows_per_rank, int K, int N,
-                                                            float grad_scale, const double* __restrict__ denom,
-                                                            float beta1, float beta2, float eps,
-                                                            const float* __restrict__ state) {
+constexpr int AF_ROWS = 4;                 // rows per thread
+constexpr int AF_TK = 4 * AF_ROWS;         // rows per CTA
+
+__global__ void __launch_bounds__(256, 2) adam_factored_kernel(float* __restrict__ w, float* __restrict__ m,
+                                                               float* __restrict__ v, int ldw, Factor fx, Factor fz,
+                                                               int Bt, int rows_per_rank, int K, int N,
+                                                               float grad_scale, const double* __restrict__ denom,
+                                                               float beta1, float beta2, float eps,
+                                                               const float* __restrict__ state) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) float xs[16][32];
+  __shared__ __align__(16) float xs[16][AF_TK];
   __shared__ __align__(16) float zs[16][256];
   const int tid = threadIdx.x, tn = tid & 63, tk = tid >> 6;
-  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 256;
+  const int k0 = blockIdx.y * AF_TK, n0 = blockIdx.x * 256;
   const int n = n0 + 4 * tn;
-  float4 acc[8];
+  const bool col_ok = n < N;
+  float4 pp[AF_ROWS], mm[AF_ROWS], vv[AF_ROWS];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = f4_zero();
+  for (int i = 0; i < AF_ROWS; ++i) {
+    const int k = k0 + AF_ROWS * tk + i;
+    const size_t at = (size_t)k * ldw + n;
+    const bool ok = col_ok && k < K;
+    pp[i] = ldg_f4_pred(reinterpret_cast<const float4*>(w + at), ok);
+    mm[i] = ldg_f4_pred(reinterpret_cast<const float4*>(m + at), ok);
+    vv[i] = ldg_f4_pred(reinterpret_cast<const float4*>(v + at), ok);
+  }
+  float4 acc[AF_ROWS];
+#pragma unroll
+  for (int i = 0; i < AF_ROWS; ++i) acc[i] = f4_zero();
   for (int b0 = 0; b0 < Bt; b0 += 16) {
-    if (tid < 128) {
-      const int bb = tid >> 3, c = tid & 7;
+    if (tid < 16 * AF_TK / 4) {                        // x chunk: 16 rows x AF_TK columns as float4
+      const int bb = tid / (AF_TK / 4), c = tid - bb * (AF_TK / 4);
       const int k = k0 + 4 * c;
       const bool ok = b0 + bb < Bt && k < K;
       const float* row = ok ? factor_row(fx, b0 + bb, rows_per_rank) : fx.base;
       *reinterpret_cast<float4*>(&xs[bb][4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + k), ok);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 4; ++r) {                      // dz chunk: 16 x 256 floats as float4
       const int idx = tid + 256 * r;
       const int bb = idx >> 6, c = idx & 63;
       const int nn = n0 + 4 * c;
@@ -194,33 +212,19 @@ __global__ void __launch_bounds__(256) adam_factored_kernel(float* __restrict__ 
 #pragma unroll
     for (int bb = 0; bb < 16; ++bb) {
       const float4 zv = *reinterpret_cast<const float4*>(&zs[bb][4 * tn]);
-      const float4 x0 = *reinterpret_cast<const float4*>(&xs[bb][8 * tk]);
-      const float4 x1 = *reinterpret_cast<const float4*>(&xs[bb][8 * tk + 4]);
+      const float4 x0 = *reinterpret_cast<const float4*>(&xs[bb][AF_ROWS * tk]);
       acc[0] = f4_fma(x0.x, zv, acc[0]); acc[1] = f4_fma(x0.y, zv, acc[1]);
       acc[2] = f4_fma(x0.z, zv, acc[2]); acc[3] = f4_fma(x0.w, zv, acc[3]);
-      acc[4] = f4_fma(x1.x, zv, acc[4]); acc[5] = f4_fma(x1.y, zv, acc[5]);
-      acc[6] = f4_fma(x1.z, zv, acc[6]); acc[7] = f4_fma(x1.w, zv, acc[7]);
     }
     __syncthreads();
   }
-  if (n >= N) return;
+  if (!col_ok) return;
   if (denom) grad_scale /= (float)(*denom);
   const float gs = grad_scale * state[4];            // 1/n normalisation times the clip scale
   const float lr_t = state[3];
   const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
-  // all loads of the thread's rows first, then the arithmetic, then the stores
-  float4 pp[8], mm[8], vv[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = k0 + 8 * tk + i;
-    const size_t at = (size_t)k * ldw + n;
-    const bool ok = k < K;
-    pp[i] = ok ? *reinterpret_cast<const float4*>(w + at) : f4_zero();
-    mm[i] = ok ? *reinterpret_cast<const float4*>(m + at) : f4_zero();
-    vv[i] = ok ? *reinterpret_cast<const float4*>(v + at) : f4_zero();
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < AF_ROWS; ++i) {
     float pa[4] = {pp[i].x, pp[i].y, pp[i].z, pp[i].w};
     float ma[4] = {mm[i].x, mm[i].y, mm[i].z, mm[i].w};
     float va[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
@@ -232,18 +236,12 @@ __global__ void __launch_bounds__(256) adam_factored_kernel(float* __restrict__ 
       va[c] = va[c] + (gk * gk - va[c]) * omb2;
       pa[c] = pa[c] - (ma[c] * lr_t) / (sqrtf(va[c]) + eps);
     }
-    pp[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-    mm[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
-    vv[i] = make_float4(va[0], va[1], va[2], va[3]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = k0 + 8 * tk + i;
+    const int k = k0 + AF_ROWS * tk + i;
     if (k < K) {
       const size_t at = (size_t)k * ldw + n;
-      *reinterpret_cast<float4*>(w + at) = pp[i];
-      *reinterpret_cast<float4*>(m + at) = mm[i];
-      *reinterpret_cast<float4*>(v + at) = vv[i];
+      *reinterpret_cast<float4*>(w + at) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+      *reinterpret_cast<float4*>(m + at) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+      *reinterpret_cast<float4*>(v + at) = make_float4(va[0], va[1], va[2], va[3]);
     }
   }
 }
@@ -465,7 +463,7 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
       (((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)x | (uintptr_t)dz) & 15))
     return DINCAE_EINVAL;
   Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
-  launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, 32)), 256, 0, (cudaStream_t)stream, w, m, v, ldw,
+  launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v, ldw,
            fx, fz, world * rows_per_rank, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state);
   return check_launch();
 }

@@ -218,6 +218,23 @@ int dincae_dense_bwd_data(const float* dz, const float* w, const float* act_in,
 int dincae_dense_bwd_weight(const float* x, const float* dz, int B, int K, int N,
                             float* dw, float* db, void* stream);
 
+/* ---- dense bottleneck on the tensor cores (bf16 path) ---------------------------------------------
+ * tf.layers.dense forward and its data gradient (DINCAE/__init__.py:479-483) as tcgen05.mma
+ * kind::f16 GEMMs over a TILED bf16 copy of the kernel, w8 [K/8][N/8][8 k][8 n] (K, N multiples of 8;
+ * dincae_dense_tc_tile_weights makes it from the fp32 master [K][ldw]; the factored Adam kernel
+ * can keep it up to date).  One copy serves both products.  x / dz / outputs stay fp32 row-major
+ * (row pitches ldx / ldy / lddz / lddx); B <= 256.  fp32 accumulation; bias / ReLU / ReLU gate as in
+ * dincae_dense_fwd / dincae_dense_bwd_data.  workspace: dincae_dense_tc_workspace() bytes. */
+size_t dincae_dense_tc_weights_elems(int K, int N);
+int dincae_dense_tc_tile_weights(const float* w, int ldw, int K, int N, void* w8, void* stream);
+size_t dincae_dense_tc_workspace(int B, int K, int N);
+int dincae_dense_tc_fwd(const float* x, int ldx, const void* w8, const float* bias, int B, int K, int N,
+                        int relu, float* y, int ldy, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int dincae_dense_tc_bwd_data(const float* dz, int lddz, const void* w8, const float* act_in, int B, int K,
+                             int N, float* dx, int lddx, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* ---- dense-bottleneck gradients in factored form (new capability) ------------------------------
  * The gradient of a dense kernel is dW = x^T dz (x [Bt,K]: the layer input, dz [Bt,N]: gradient of
  * its pre-activation, Bt frames of the GLOBAL batch).  These entry points let the optimiser work
