@@ -66,7 +66,7 @@ SIGNATURES = {
                                             vp, vp, c_size_t, vp]),
     "dincae_adam_update_factored": (c_int, [vp, vp, vp, c_int, vp, c_size_t, c_int, vp, c_size_t, c_int,
                                             c_int, c_int, c_int, c_int, c_float, vp, c_float, c_float, c_float,
-                                            vp, vp]),
+                                            vp, vp, vp]),
     "dincae_dense_factored_expand": (c_int, [vp, c_size_t, c_int, vp, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                              vp, c_int, vp]),
     "dincae_dense_bias_grad": (c_int, [vp, c_int, c_int, c_int, vp, vp]),

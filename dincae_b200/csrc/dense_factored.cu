@@ -14,7 +14,7 @@
 //     all-reducing dW; every rank then applies the same update in the same order.
 // Rows of the factors live in `world` per-rank blocks (row bt -> rank bt / rows_per_rank): the
 // all-gathered buffer is used in place.
-#include "common.cuh"
+#include "bf16.cuh"
 #include "umma.cuh"
 #include <math.h>
 
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(256, 2) adam_factored_kernel(float* __restrict
                                                                int Bt, int rows_per_rank, int K, int N,
                                                                float grad_scale, const double* __restrict__ denom,
                                                                float beta1, float beta2, float eps,
-                                                               const float* __restrict__ state) {
+                                                               const float* __restrict__ state,
+                                                               uint2* __restrict__ w8) {
   pdl_trigger();
   pdl_wait();
   __shared__ __align__(16) float xs[16][AF_TK];
@@ -218,7 +219,6 @@ __global__ void __launch_bounds__(256, 2) adam_factored_kernel(float* __restrict
     }
     __syncthreads();
   }
-  if (!col_ok) return;
   if (denom) grad_scale /= (float)(*denom);
   const float gs = grad_scale * state[4];            // 1/n normalisation times the clip scale
   const float lr_t = state[3];
@@ -237,11 +237,32 @@ __global__ void __launch_bounds__(256, 2) adam_factored_kernel(float* __restrict
       pa[c] = pa[c] - (ma[c] * lr_t) / (sqrtf(va[c]) + eps);
     }
     const int k = k0 + AF_ROWS * tk + i;
-    if (k < K) {
+    if (k < K && col_ok) {
       const size_t at = (size_t)k * ldw + n;
       *reinterpret_cast<float4*>(w + at) = make_float4(pa[0], pa[1], pa[2], pa[3]);
       *reinterpret_cast<float4*>(m + at) = make_float4(ma[0], ma[1], ma[2], ma[3]);
       *reinterpret_cast<float4*>(v + at) = make_float4(va[0], va[1], va[2], va[3]);
+      // tiled bf16 copy for the tensor-core GEMMs (dense_tc.cu), staged in shared memory (the zs
+      // buffer is free by now) so that it leaves the SM as whole 128-byte blocks
+      if (w8)
+        reinterpret_cast<uint2*>(&zs[0][0])[(((AF_ROWS * tk + i) >> 3) * 32 + tn / 2) * 16 +
+                                            ((AF_ROWS * tk + i) & 7) * 2 + (tn & 1)] =
+            make_uint2(bf2_pack(pa[0], pa[1]), bf2_pack(pa[2], pa[3]));
+    }
+  }
+  if (w8) {
+    // CTA tile = 16 rows x 256 columns = 2 k-blocks x 32 n-blocks of 128 bytes: [kb][nb][8][8] in
+    // shared memory, copied out 16 bytes per thread and pass (two passes), whole blocks contiguous
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(&zs[0][0]);
+    const int NB = N >> 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + 256 * r;                   // 16-byte unit: kb * 256 + nb * 8 + row
+      const int kb = idx >> 8, nb = (idx >> 3) & 31, row = idx & 7;
+      const int k = k0 + 8 * kb + row, nn = n0 + 8 * nb;
+      if (k < K && nn < N)
+        reinterpret_cast<uint4*>(w8)[((size_t)(k >> 3) * NB + (nn >> 3)) * 8 + row] = src[idx];
     }
   }
 }
@@ -457,14 +478,16 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
                                            const float* dz, size_t dz_rank_stride, int lddz,
                                            int world, int rows_per_rank, int K, int N,
                                            float grad_scale, const double* denom, float beta1, float beta2,
-                                           float eps, const float* state, void* stream) {
+                                           float eps, const float* state, void* w8, void* stream) {
   if (!w || !m || !v || !x || !dz || !state || world <= 0 || rows_per_rank <= 0 || K <= 0 || N <= 0) return DINCAE_EINVAL;
+  if (w8 && ((K & 7) || (N & 7))) return DINCAE_EINVAL;
   if ((ldw & 3) || (N & 3) || (K & 3) || (ldx & 3) || (lddz & 3) || (x_rank_stride & 3) || (dz_rank_stride & 3) ||
       (((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)x | (uintptr_t)dz) & 15))
     return DINCAE_EINVAL;
   Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
   launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v, ldw,
-           fx, fz, world * rows_per_rank, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state);
+           fx, fz, world * rows_per_rank, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
+           reinterpret_cast<uint2*>(w8));
   return check_launch();
 }
 

@@ -52,7 +52,7 @@ class Plan:
         self.dense_pad = [self.n_flat]
         for i, u in enumerate(self.dense_units):
             last = i == len(self.dense_units) - 1
-            self.dense_pad.append(self.n_flat if last else layout.round_up(u, 4))
+            self.dense_pad.append(self.n_flat if last else layout.round_up(u, self.lanes))
         self._build_params()
 
     def _planes(self, c):
@@ -624,11 +624,12 @@ class Network:
             e = self._ent[("dense" if i == 0 else "dense_%d" % i) + "/kernel"]
             o = e["offset"]
             kk, nn = e["tf_shape"]
+            w8 = self.w8[i] if getattr(self, "w8", None) else None
             self._call("adam_dense_factored(%d)" % i, "dincae_adam_update_factored", (
                 ptr(self.params[o:]), ptr(self.adam_m[o:]), ptr(self.adam_v[o:]), f["N"],
                 base + 4 * f["x"], L, f["K"], base + 4 * f["z"], L, f["N"], self.world, B, f["K"], f["N"],
-                grad_scale, ptr(denom), beta1, beta2, eps, ptr(self.adam_state), st),
-                24 * kk * nn, 2 * self.world * B * kk * nn)
+                grad_scale, ptr(denom), beta1, beta2, eps, ptr(self.adam_state), ptr(w8), st),
+                (26 if w8 is not None else 24) * kk * nn, 2 * self.world * B * kk * nn)
 
 
 def make_network(plan, max_batch, train=True, device=None, **kw):
@@ -715,7 +716,10 @@ class NetworkBF16(Network):
             self._wbf[name] = info
         self.wbf = torch.zeros(total, **b16)
 
-        ws = [self.lib.dincae_dense_workspace(B, P.dense_pad[i], P.dense_pad[i + 1]) for i in range(nd)]
+        # tiled bf16 copies of the dense kernels for the tensor-core GEMMs (csrc/dense_tc.cu)
+        self.w8 = [torch.zeros(P.dense_pad[i] * P.dense_pad[i + 1], **b16) for i in range(nd)]
+        ws = [self.lib.dincae_dense_tc_workspace(min(B, 256), P.dense_pad[i], P.dense_pad[i + 1]) for i in range(nd)]
+        ws += [self.lib.dincae_dense_workspace(B, P.dense_pad[i], P.dense_pad[i + 1]) for i in range(nd)]
         if train:
             self.S8 = [None] + [
                 torch.zeros(B, P.ep8[l], P.sizes[l - 1][0], 4 * ((P.sizes[l - 1][1] + 3) // 4),
@@ -772,9 +776,25 @@ class NetworkBF16(Network):
         off, n = self._wbf[name]["wf"]
         return self.wbf[off: off + n]
 
+    def tile_dense_weights(self):
+        """fp32 master dense kernels -> tiled bf16 copies."""
+        P, st = self.plan, stream_ptr()
+        for i in range(len(P.dense_units)):
+            name = "dense" if i == 0 else "dense_%d" % i
+            K, N = P.dense_pad[i], P.dense_pad[i + 1]
+            self._call("dense_tile_weights(%d)" % i, "dincae_dense_tc_tile_weights", (
+                ptr(self._w(name + "/kernel")), N, K, N, ptr(self.w8[i]), st), 6 * K * N, 0)
+
+    def set_params_tf(self, tf_params):
+        super().set_params_tf(tf_params)
+        self.tile_dense_weights()
+
     def prepare_weights(self):
-        """fp32 master kernels -> bf16 operand copies (one small launch per layer and copy)."""
+        """fp32 master kernels -> bf16 operand copies (one small launch per layer and copy).  The
+        dense copies are refreshed here too unless the factored Adam kernel keeps them current."""
         st = stream_ptr()
+        if not self.factored and self.train:
+            self.tile_dense_weights()
         for name, info in self._wbf.items():
             e = self._ent[name + "/kernel"]
             w = self._w(e["name"])
@@ -820,11 +840,19 @@ class NetworkBF16(Network):
         for i in range(nd):
             name = "dense" if i == 0 else "dense_%d" % i
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
-            self._call("dense_fwd(%d)" % i, "dincae_dense_fwd", (
-                ptr(self.F[i]), ptr(self._w(name + "/kernel")), ptr(self._w(name + "/bias")),
-                B, P.dense_pad[i], P.dense_pad[i + 1], 1, ptr(self.F[i + 1]),
-                ptr(self.workspace), self.workspace.numel(), st),
-                4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
+            K, N = P.dense_pad[i], P.dense_pad[i + 1]
+            if B <= 256:
+                # tensor cores over the tiled bf16 copy: one pass over 2 bytes per weight
+                self._call("dense_fwd(%d)" % i, "dincae_dense_tc_fwd", (
+                    ptr(self.F[i]), K, ptr(self.w8[i]), ptr(self._w(name + "/bias")), B, K, N, 1,
+                    ptr(self.F[i + 1]), N, ptr(self.workspace), self.workspace.numel(), st),
+                    4 * (B * kk + B * nn) + 2 * kk * nn, 2 * B * kk * nn)
+            else:
+                self._call("dense_fwd(%d)" % i, "dincae_dense_fwd", (
+                    ptr(self.F[i]), ptr(self._w(name + "/kernel")), ptr(self._w(name + "/bias")),
+                    B, K, N, 1, ptr(self.F[i + 1]),
+                    ptr(self.workspace), self.workspace.numel(), st),
+                    4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
         if nd:
             self._call("p4_to_p8(bottleneck)", "dincae_p4_to_p8", (
                 ptr(self.F[nd]), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.D8[0]), st),
@@ -904,10 +932,15 @@ class NetworkBF16(Network):
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
             self._dense_weight_grad(i, B)
             dst = self.dZ[i] if i > 0 else self.dF0
-            self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
-                ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
-                ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
-                4 * (B * nn + kk * nn + B * kk), 2 * B * kk * nn)
+            if B <= 256:
+                self._call("dense_bwd_data(%d)" % i, "dincae_dense_tc_bwd_data", (
+                    ptr(self.dZ[i + 1]), N, ptr(self.w8[i]), ptr(self.F[i]) if i > 0 else None, B, K, N,
+                    ptr(dst), K, wsp, wsn, st), 4 * (B * nn + B * kk) + 2 * kk * nn, 2 * B * kk * nn)
+            else:
+                self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
+                    ptr(self.dZ[i + 1]), ptr(self._w(name + "/kernel")),
+                    ptr(self.F[i]) if i > 0 else None, B, K, N, ptr(dst), wsp, wsn, st),
+                    4 * (B * nn + kk * nn + B * kk), 2 * B * kk * nn)
         if nd:
             self._call("p4_to_p8(bottleneck grad)", "dincae_p4_to_p8", (
                 ptr(self.dF0), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.dX8[L]), st),

@@ -246,7 +246,8 @@ int dincae_dense_tc_bwd_data(const float* dz, int lddz, const void* w8, const fl
  * i.e. an all-gathered buffer of per-rank blobs is used in place (world = 1: a plain matrix).
  *   dense_factored_sumsq : *sumsq += ||x^T dz||_F^2 = sum_{b,b'} (x_b.x_b')(dz_b.dz_b') (fixed order).
  *   adam_update_factored : TF-Adam on w [K][ldw] (N columns) with g = x^T dz * grad_scale / *denom *
- *                          state[4] (clip scale), lr_t = state[3] -- the scalars adam_step_multi left.
+ *                          state[4] (clip scale), lr_t = state[3] -- the scalars adam_step_multi left;
+ *                          w8 != NULL: also refreshes the tiled bf16 copy of dincae_dense_tc_*.
  *   dense_factored_expand: dw [K][ldw] = x^T dz (tests / callers that want the matrix).
  *   dense_bias_grad      : db[n] = sum_b dz[b][n] over the B rows (row pitch ld) of one rank.
  *   adam_step_multi      : global norm + TF-Adam over n parameters whose gradient is given as `world`
@@ -264,7 +265,7 @@ int dincae_adam_update_factored(float* w, float* m, float* v, int ldw,
                                 const float* dz, size_t dz_rank_stride, int lddz,
                                 int world, int rows_per_rank, int K, int N,
                                 float grad_scale, const double* denom, float beta1, float beta2,
-                                float eps, const float* state, void* stream);
+                                float eps, const float* state, void* w8, void* stream);
 int dincae_dense_factored_expand(const float* x, size_t x_rank_stride, int ldx,
                                  const float* dz, size_t dz_rank_stride, int lddz,
                                  int world, int rows_per_rank, int K, int N, float* dw, int ldw,

@@ -51,7 +51,7 @@ def test_factor_ops_match_the_materialised_gradient(world, rows, K, N):
     denom = torch.tensor([7.0], dtype=torch.float64, device="cuda")
     w, m, v = w0.clone(), m0.clone(), v0.clone()
     check(lib.dincae_adam_update_factored(ptr(w), ptr(m), ptr(v), N, xb, stride, K, zb, stride, N, world, rows, K, N,
-                                          1.5, ptr(denom), 0.9, 0.999, 1e-8, ptr(state), stream()))
+                                          1.5, ptr(denom), 0.9, 0.999, 1e-8, ptr(state), None, stream()))
     torch.cuda.synchronize()
     gk = dw.float().cuda() * (1.5 / 7.0) * 0.37
     m_ref = m0 + (gk - m0) * 0.1
@@ -140,3 +140,23 @@ def test_network_factored_equals_materialised(case, lanes):
     pa, pb = nets[0].params.cpu(), nets[1].params.cpu()
     # Adam normalises steps, so an entry whose gradient is at rounding level may differ by a step
     assert float((pa - pb).abs().max()) < 2.1e-3 and float((pa - pb).abs().mean()) < 1e-6
+
+
+@pytest.mark.parametrize("rows,K,N", [(5, 136, 72), (16, 2648, 536), (50, 536, 2648)])
+def test_factored_adam_keeps_the_tiled_bf16_copy_current(rows, K, N):
+    """adam_update_factored(w8=...) leaves w8 == tile(bf16(updated w)), the operand of dense_tc.cu."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(rows + K)
+    x = torch.randn(rows, K, generator=g).cuda()
+    dz = torch.randn(rows, N, generator=g).cuda()
+    w = torch.randn(K, N, generator=g).cuda()
+    m = torch.zeros(K, N, device="cuda")
+    v = torch.zeros(K, N, device="cuda")
+    state = torch.tensor([0.9, 0.999, 0.0, 1e-2, 1.0, 0, 0, 0], dtype=torch.float32, device="cuda")
+    w8 = torch.zeros(K * N, dtype=torch.bfloat16, device="cuda")
+    check(lib.dincae_adam_update_factored(ptr(w), ptr(m), ptr(v), N, ptr(x), rows * K, K, ptr(dz), rows * N, N, 1, rows,
+                                          K, N, 1.0, None, 0.9, 0.999, 1e-8, ptr(state), ptr(w8), stream()))
+    ref8 = torch.zeros_like(w8)
+    check(lib.dincae_dense_tc_tile_weights(ptr(w), N, K, N, ptr(ref8), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(w8, ref8)

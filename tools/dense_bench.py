@@ -53,7 +53,7 @@ for (k, n) in ((K, N), (N, K)):
     ss = torch.zeros(1, dtype=torch.float64, device="cuda")
     ms = timeit(lambda: check(lib.dincae_adam_update_factored(
         ptr(w), ptr(m), ptr(v), n, ptr(xf), B * k, k, ptr(zf), B * n, n, world, B, k, n, 1.0, None, 0.9, 0.999,
-        1e-8, ptr(state), st)))
+        1e-8, ptr(state), None, st)))
     print("adam_factored  Bt=%d %dx%d  %7.3f ms  %6.0f GB/s (24 B/param)" % (world * B, k, n, ms, 24.0 * k * n / ms / 1e6),
           flush=True)
     ms = timeit(lambda: check(lib.dincae_dense_factored_sumsq(
