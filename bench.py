@@ -70,7 +70,8 @@ def parse():
     ap.add_argument("--steps-d", type=int, default=0, help="timed steps of the 512x512 leg (default min(steps, 20))")
     ap.add_argument("--no-e2e-api", action="store_true",
                     help="time e2e through Trainer.train_step instead of DINCAE.reconstruct_gridded_nc")
-    ap.add_argument("--e2e-epochs", type=int, default=0)
+    ap.add_argument("--e2e-epochs", type=int, default=100,
+                    help="epochs of the e2e run through DINCAE.reconstruct_gridded_nc (reference default: 1000)")
     return ap.parse_args()
 
 
@@ -420,6 +421,9 @@ def e2e_api_leg(a, world, rank, dist, barrier, K):
     d = box[0]
     fname, outdir = os.path.join(d, "sst.nc"), os.path.join(d, "out")
     spe = ceil(a.ntime / (a.batch * world))
+    # The reference trains epochs=1000 by default (DINCAE/__init__.py:307); 100 keeps the bench
+    # short.  Every one-off cost of the call (netCDF read, upload, kernel / graph set-up, the final
+    # reconstruction and its file) is inside the timed region and is amortised over these epochs.
     E = a.e2e_epochs if a.e2e_epochs > 0 else max(1, ceil(K / spe))
     loss = []
     barrier()

@@ -75,7 +75,13 @@ def load_gridded_nc(fname, varname, minfrac=0.05):
     else:
         missing = data.mask
     print("data shape: ", data.shape)
-    print("data range: ", data.min(), data.max())
+    # same print as the reference (:113); np.ma's min / max copy the cube twice (0.33 s for the
+    # 5266-frame cube), the where= reductions do not
+    raw, valid = np.ma.getdata(data), ~missing
+    if valid.any():
+        print("data range: ", raw.min(where=valid, initial=np.inf), raw.max(where=valid, initial=-np.inf))
+    else:
+        print("data range: ", np.ma.masked, np.ma.masked)
     return lon, lat, time, data, missing, mask
 
 
@@ -315,15 +321,28 @@ def reconstruct(lon, lat, mask, meandata,
             raise ValueError("data-parallel runs need the generators of data_generator / "
                              "data_generator_list (the batch is built on each rank's GPU)")
         from .hostfeed import reconstruct_from_generators
-        return reconstruct_from_generators(
-            plan, lon, lat, mask, meandata, train_datagen, train_len, test_datagen, test_len,
-            outdir, epochs=epochs, batch_size=batch_size, save_each=save_each,
-            truth_uncertain=truth_uncertain, shuffle_buffer_size=shuffle_buffer_size,
-            clip_grad=clip_grad, regularization_L2_beta=regularization_L2_beta, transfun=transfun,
-            savesample=savesample, learning_rate=learning_rate,
-            learning_rate_decay_epoch=learning_rate_decay_epoch, init_seed=init_seed,
-            shuffle_seed=shuffle_seed, loss=loss, output_name=_output_name,
-            close_writer=_close_writer)
+        writer_hf = None
+        if tensorboard and outdir is not None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                writer_hf = SummaryWriter(os.path.join(outdir, "train"))
+            except Exception:            # noqa: BLE001
+                writer_hf = None
+        try:
+            return reconstruct_from_generators(
+                plan, lon, lat, mask, meandata, train_datagen, train_len, test_datagen, test_len,
+                outdir, epochs=epochs, batch_size=batch_size, save_each=save_each,
+                truth_uncertain=truth_uncertain, shuffle_buffer_size=shuffle_buffer_size,
+                clip_grad=clip_grad, regularization_L2_beta=regularization_L2_beta, transfun=transfun,
+                savesample=savesample, learning_rate=learning_rate,
+                learning_rate_decay_epoch=learning_rate_decay_epoch, init_seed=init_seed,
+                shuffle_seed=shuffle_seed, loss=loss, output_name=_output_name,
+                close_writer=_close_writer, iseed=iseed, nepoch_keep_missing=nepoch_keep_missing,
+                save_model_each=save_model_each, save_checkpoint=save_checkpoint,
+                tensorboard_writer=writer_hf)
+        finally:
+            if writer_hf is not None:
+                writer_hf.close()
 
     cube = train_datagen.cube()
     test_cube = test_datagen.cube()
