@@ -9,7 +9,7 @@ fails loudly if the CUDA extension (libdincae_b200.so) is missing -- there is no
 """
 from .api import (FrameSource, NEAREST_NEIGHBOR, data_generator, data_generator_list, identity,
                   load_checkpoint, load_gridded_nc, reconstruct, reconstruct_gridded_files,
-                  reconstruct_gridded_nc, save_checkpoint, savesample, set_precision, get_precision, sinv)
+                  reconstruct_gridded_nc, save_checkpoint, savesample, set_precision, get_precision, set_dropout_active, sinv)
 from .ensemble import EnsembleAccumulator, average_reconstructions
 
 __all__ = ["reconstruct", "load_gridded_nc", "data_generator", "reconstruct_gridded_nc"]

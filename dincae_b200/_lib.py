@@ -61,6 +61,8 @@ SIGNATURES = {
     "dincae_dense_tc_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_dense_tc_fwd": (c_int, [vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, c_int, vp, c_size_t, vp]),
     "dincae_dense_tc_bwd_data": (c_int, [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, vp, c_size_t, vp]),
+    "dincae_dropout_fwd": (c_int, [vp, c_int, c_int, c_int, c_float, c_uint64, c_uint64, c_int, vp, vp, vp]),
+    "dincae_scale_rows": (c_int, [vp, c_int, c_int, c_int, c_float, vp]),
     "dincae_dense_factored_workspace": (c_size_t, [c_int, c_int, c_int]),
     "dincae_dense_factored_sumsq": (c_int, [vp, c_size_t, c_int, vp, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                             vp, vp, c_size_t, vp]),

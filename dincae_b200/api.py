@@ -31,6 +31,17 @@ def set_precision(name):
     _precision[0] = name
 
 
+_dropout_active = [False]
+
+
+def set_dropout_active(active):
+    """``True``: ``dropout_rate_train`` of `reconstruct` drops units after every dense layer while
+    training (what the reference's tf.layers.dropout call was meant to do).  Default ``False`` =
+    the reference's actual behaviour: the layer is inert because it is called without
+    ``training=True`` (DINCAE/__init__.py:483)."""
+    _dropout_active[0] = bool(active)
+
+
 def get_precision():
     name = _precision[0] or os.environ.get("DINCAE_PRECISION", "tf32").lower()
     if name not in ("tf32", "bf16", "fp32"):
@@ -188,9 +199,22 @@ def savesample(fname, m_rec, σ2_rec, meandata, lon, lat, e, ii, offset,
         w = ncio.ReconWriter(fname, lon, lat, meandata, append=(ii != 0 and os.path.isfile(fname)))
         _open_writers[fname] = w
     w.write(offset, np.asarray(recdata), np.asarray(sigma_rec))
+    # the reference opens and closes the file per call (:279-294): the file must be complete after
+    # every call here as well (record count in the header), whoever closes the writer later
+    w.sync()
 
 
 _open_writers = {}
+
+
+def _close_all_writers():
+    for name in list(_open_writers):
+        _close_writer(name)
+
+
+import atexit  # noqa: E402
+
+atexit.register(_close_all_writers)
 
 
 def _close_writer(fname):
@@ -258,8 +282,9 @@ def reconstruct(lon, lat, mask, meandata,
 
     Differences that do not change results: ``dropout_rate_train`` and ``nprefetch`` are
     accepted and ignored (dropout never fires in the reference; the feed is
-    on the GPU); only nearest-neighbour ``resize_method`` exists; ``tensorboard`` writes
-    scalars only when ``torch.utils.tensorboard`` is importable.
+    on the GPU); only nearest-neighbour ``resize_method`` exists (anything else raises, see
+    INTEGRATION.md); ``tensorboard`` writes the reference's scalars and images (:575-584) through
+    ``torch.utils.tensorboard`` when it is importable.
 
     New capability: inside an initialised ``torch.distributed`` group
     of N > 1 ranks (one process per GPU) training is data parallel -- every rank builds
@@ -352,7 +377,8 @@ def reconstruct(lon, lat, mask, meandata,
     trainer = Trainer(plan, cube, batch_size, truth_uncertain=truth_uncertain,
                       clip_grad=clip_grad, l2_beta=regularization_L2_beta,
                       noise_seed=noise_seed, init_seed=init_seed,
-                      jitter_std=train_datagen.jitter_std, dist_group=True if dist is not None else None)
+                      jitter_std=train_datagen.jitter_std, dist_group=True if dist is not None else None,
+                      dropout_rate=dropout_rate_train if _dropout_active[0] else 0.0)
     sampler = TrainSampler(train_len, batch_size * world, shuffle_buffer_size, seed=shuffle_seed,
                            py_random=py_random, train=train_datagen.train)
     mine = slice(rank * batch_size, (rank + 1) * batch_size)
@@ -381,6 +407,43 @@ def reconstruct(lon, lat, mask, meandata,
     index = 0
     steps_per_epoch = ceil(train_len / (batch_size * world))
 
+    # TensorBoard images of the reference (:578-584): m_rec, m_true, sigma2_rec of the first 3
+    # frames of every training batch, times the land-sea mask, flipped upside down, scaled to uint8
+    # the way tf.summary.image scales float images.  The frames go through a small pinned ring and
+    # are written when it is full / at the end of an epoch, so the step loop never synchronises.
+    img_k = min(3, batch_size)
+    img_ring, img_pending, img_index = None, [], 0
+    if writer_tb is not None:
+        img_ring = [torch.zeros(3, img_k, jmax, imax).pin_memory() for _ in range(32)]
+        issea = torch.from_numpy(np.asarray(mask, dtype=np.float32)).to(trainer.net.dev)
+
+    def snapshot_images():
+        nonlocal img_index
+        net = trainer.net
+        if len(img_pending) == len(img_ring):
+            flush_images()
+        net.head_recon(img_k)
+        xt = net.xtrue[:img_k]
+        s2t = 1.0 / torch.clamp(xt[..., 1], min=1e-3)                 # :524-527
+        buf = img_ring[len(img_pending)]
+        buf[0].copy_(net.m_rec[:img_k] * issea, non_blocking=True)
+        buf[1].copy_(xt[..., 0] * s2t * issea, non_blocking=True)
+        buf[2].copy_(net.s2_rec[:img_k] * issea, non_blocking=True)
+        img_pending.append(img_index)
+        img_index += 1
+
+    def flush_images():
+        if not img_pending:
+            return
+        torch.cuda.current_stream().synchronize()
+        for slot, step in enumerate(img_pending):
+            arr = img_ring[slot].numpy()
+            for name, a in zip(("m_rec", "m_true", "sigma2_rec"), arr):
+                for j in range(img_k):
+                    writer_tb.add_image("Validation/%s/image/%d" % (name, j), _tf_image_u8(a[j][::-1])[None],
+                                        step, dataformats="CHW")
+        del img_pending[:]
+
     def drain(e, first_step):
         nonlocal index
         for k, (c, r) in enumerate(trainer.flush_losses()):
@@ -404,7 +467,11 @@ def reconstruct(lon, lat, mask, meandata,
             if world > 1:
                 fi, ci, seq = fi[mine], ci[mine], seq[mine]
             trainer.train_step(fi, ci, seq)
+            if img_ring is not None:
+                snapshot_images()
         drain(e, 0)
+        if img_ring is not None:
+            flush_images()
 
         if ((e == epochs - 1) or ((save_each > 0) and (e % save_each == 0))) and outdir is not None:
             say("Save output", e)
@@ -427,6 +494,7 @@ def reconstruct(lon, lat, mask, meandata,
                 dist.barrier()                                   # rank 0 runs the hook path alone
             else:
                 pending = None
+                recon.begin_sweep()
                 for ii, frames in enumerate(sequential_batches(test_len, batch_size)):
                     out = recon.run_batch(frames, slot=ii % 2)
                     if pending is not None:
@@ -449,6 +517,20 @@ def reconstruct(lon, lat, mask, meandata,
     say(dt_end)
     say(dt_end - dt_start)
     return fname
+
+
+def _tf_image_u8(img):
+    """float image -> uint8 like tf.summary.image (tensorflow/core/kernels/summary_image_op.cc):
+    all values >= 0: scaled so that the largest is 255; otherwise 0 maps to 128 and the largest
+    magnitude to +-127."""
+    img = np.asarray(img, dtype=np.float32)
+    lo, hi = float(img.min()), float(img.max())
+    if lo < 0:
+        mx = max(abs(lo), abs(hi))
+        scale, offset = (127.0 / mx if mx > 1e-6 else 0.0), 128.0
+    else:
+        scale, offset = (255.0 / hi if hi > 1e-6 else 0.0), 0.0
+    return np.clip(img * scale + offset, 0, 255).astype(np.uint8)
 
 
 _SAVE_SLOTS, _SAVE_THREADS = 6, 3
@@ -492,6 +574,8 @@ def _save_records(recon, fname, lon, lat, meandata, test_len, batch_size, rank=0
         writer.write_records(offset, buf.numpy().reshape(-1).view(np.uint8), n)
 
     futures = [None] * nslots
+    if hasattr(recon, "begin_sweep"):
+        recon.begin_sweep()
     if getattr(recon, "use_graph", False):
         # graphs of every batch size of this range (full batches + the tail) are captured before
         # the writer threads start: a capture must not overlap their event waits

@@ -1,6 +1,7 @@
 // Input pipeline on the device: temporal-mean removal and the per-batch channel stacking,
 // added-cloud masking and jitter of DINCAE/__init__.py:155-227.  HBM-bound gather kernels.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace dincae {
 
@@ -93,24 +94,6 @@ __global__ void __launch_bounds__(256) cube_anom_kernel(const float* __restrict_
     const size_t p = i % HW;
     anom[i] = cube_anom1(data[i], missing[i] != 0, meandata[p], never[p] != 0, obs_var);
   }
-}
-
-// ---------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. 2011) + Box-Muller: counter-based normals so that the noise
-// of a frame depends only on (seed, sequence number of the frame, pixel, slot) and not on
-// batch composition or GPU count.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
 }
 
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {

@@ -277,6 +277,31 @@ class Network:
         self._conv_names = [e["name"][:-7] for e in P.entries if e["kind"] == "conv_w"]
         self.tracer = None       # optional callable(label, fn, args, alg_bytes, alg_flops)
 
+    # ---- dropout (optional; inert in the reference) -------------------------------------
+    dropout_rate = 0.0          # > 0: tf.layers.dropout as it was meant to act, after each dense layer
+    dropout_seed = 0
+    dropout_keys = None         # device int64 [B]: per-frame keys (the trainer's noise sequence numbers)
+    dropout_masks = None        # optional list of uint8 [B, N] tensors that receive the keep masks
+
+    def _dropout_fwd(self, i, B):
+        """Dropout on the output of dense layer i (training forward only)."""
+        if self.dropout_rate <= 0.0:
+            return
+        N = self.plan.dense_pad[i + 1]
+        mk = self.dropout_masks[i] if self.dropout_masks is not None else None
+        self._call("dropout_fwd(%d)" % i, "dincae_dropout_fwd", (
+            ptr(self.F[i + 1]), B, N, N, float(self.dropout_rate), int(self.dropout_seed) & (2 ** 64 - 1), i, 0,
+            ptr(self.dropout_keys), ptr(mk), stream_ptr()), 8 * B * N, 0)
+
+    def _dropout_bwd(self, i, B):
+        """1 / (1 - rate) on the gradient of dense layer i's (gated) output; the mask itself is
+        applied by the ReLU gate of the kernel that produced this gradient (csrc/dropout.cu)."""
+        if self.dropout_rate <= 0.0:
+            return
+        N = self.plan.dense_pad[i + 1]
+        self._call("dropout_bwd(%d)" % i, "dincae_scale_rows", (
+            ptr(self.dZ[i + 1]), B, N, N, 1.0 / (1.0 - float(self.dropout_rate)), stream_ptr()), 8 * B * N, 0)
+
     # ---- factored dense gradients / per-rank gradient blob ---------------------------------------
     def _setup_factored(self, factored, world, rank):
         """Factored mode: everything a rank contributes to the optimiser step sits in ONE
@@ -457,6 +482,8 @@ class Network:
                 B, P.dense_pad[i], P.dense_pad[i + 1], 1, ptr(self.F[i + 1]),
                 ptr(self.workspace), self.workspace.numel(), st),
                 4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
+            if save_signs:
+                self._dropout_fwd(i, B)
         for l in range(1, P.L + 1):
             up, sk, r = P.dec_sources(l)
             h, w = P.sizes[r]
@@ -543,6 +570,7 @@ class Network:
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._dropout_bwd(i, B)
             self._dense_weight_grad(i, B)
             dst = self.dZ[i] if i > 0 else self.dX[L].view(self.Bmax, -1)
             self._call("dense_bwd_data(%d)" % i, "dincae_dense_bwd_data", (
@@ -853,6 +881,8 @@ class NetworkBF16(Network):
                     B, K, N, 1, ptr(self.F[i + 1]),
                     ptr(self.workspace), self.workspace.numel(), st),
                     4 * (B * kk + kk * nn + B * nn), 2 * B * kk * nn)
+            if save_signs:
+                self._dropout_fwd(i, B)
         if nd:
             self._call("p4_to_p8(bottleneck)", "dincae_p4_to_p8", (
                 ptr(self.F[nd]), P.ep[L], P.ep8[L], B, hL, wL, ptr(self.D8[0]), st),
@@ -930,6 +960,7 @@ class NetworkBF16(Network):
             name = "dense" if i == 0 else "dense_%d" % i
             K, N = P.dense_pad[i], P.dense_pad[i + 1]
             kk, nn = self._ent[name + "/kernel"]["tf_shape"]
+            self._dropout_bwd(i, B)
             self._dense_weight_grad(i, B)
             dst = self.dZ[i] if i > 0 else self.dF0
             if B <= 256:

@@ -253,6 +253,13 @@ class RecordFileWriter:
         rec[:, :, self.mask] = self.fill
         self.write_records(offset, rec.reshape(-1).view(np.uint8), n)
 
+    def sync(self):
+        """Make the file valid as it stands (record count in the header, no trailing
+        preallocation): for callers that append batch by batch and may never call close()."""
+        if self.fd is not None:
+            os.pwrite(self.fd, struct.pack(">i", self.numrecs), 4)
+            os.ftruncate(self.fd, self.rec_start + self.numrecs * self.recsize)
+
     def close(self, finalize=True):
         """``finalize=False``: just drop the descriptor -- for the ranks of a sharded sweep that
         wrote their record ranges into a file whose header another rank owns."""
@@ -281,6 +288,8 @@ class ReconWriter:
 
     def __init__(self, fname, lon, lat, meandata, fill_value=-9999., append=False,
                  expect_records=0):  # pragma: no cover
+        import threading
+        self._nc4_lock = threading.Lock()
         self.fname = fname
         self.fill = np.float32(fill_value)
         self.mask = np.ma.getmaskarray(np.ma.asarray(meandata)).reshape(len(lat), len(lon))
@@ -306,19 +315,27 @@ class ReconWriter:
 
     def write(self, offset, mean_rec, sigma_rec):  # pragma: no cover
         """mean_rec / sigma_rec [n,lat,lon]; entries under meandata.mask get the fill value
-        (:288-291)."""
+        (:288-291).  netCDF-C / HDF5 are not thread-safe and netCDF4-python drops the GIL inside
+        nc_put_vara: writes from the writer threads are serialised here."""
         n = mean_rec.shape[0]
         m = np.broadcast_to(self.mask, mean_rec.shape)
-        self.v_mean[offset:offset + n] = np.ma.masked_array(np.asarray(mean_rec, dtype="f4"), m)
-        self.v_sigma[offset:offset + n] = np.ma.masked_array(np.asarray(sigma_rec, dtype="f4"), m)
+        with self._nc4_lock:
+            self.v_mean[offset:offset + n] = np.ma.masked_array(np.asarray(mean_rec, dtype="f4"), m)
+            self.v_sigma[offset:offset + n] = np.ma.masked_array(np.asarray(sigma_rec, dtype="f4"), m)
+
+    def sync(self):  # pragma: no cover
+        with self._nc4_lock:
+            if self.ds is not None:
+                self.ds.sync()
 
     def write_records(self, offset, records, n=None):  # pragma: no cover
         rec = np.frombuffer(memoryview(records).cast("B"), dtype=">f4").reshape(
             -1, 2, self.mask.shape[0], self.mask.shape[1])
         n = rec.shape[0] if n is None else n
         m = np.broadcast_to(self.mask, (n,) + self.mask.shape)
-        self.v_mean[offset:offset + n] = np.ma.masked_array(rec[:n, 0].astype("f4"), m)
-        self.v_sigma[offset:offset + n] = np.ma.masked_array(rec[:n, 1].astype("f4"), m)
+        with self._nc4_lock:
+            self.v_mean[offset:offset + n] = np.ma.masked_array(rec[:n, 0].astype("f4"), m)
+            self.v_sigma[offset:offset + n] = np.ma.masked_array(rec[:n, 1].astype("f4"), m)
 
     def close(self):  # pragma: no cover
         if self.ds is not None:

@@ -22,7 +22,7 @@ from .engine import Network, make_network
 class Trainer:
     def __init__(self, plan, cube, batch_size, truth_uncertain=False, clip_grad=5.0,
                  l2_beta=0.0, noise_seed=0, use_graph=True, dist_group=None, tf_params=None,
-                 init_seed=0, jitter_std=None):
+                 init_seed=0, jitter_std=None, dropout_rate=0.0):
         self.plan, self.cube = plan, cube
         self.B = int(batch_size)
         self.truth_uncertain = bool(truth_uncertain)
@@ -68,6 +68,11 @@ class Trainer:
         self.frame_idx = self.idx_dev[:B]
         self.cloud_idx = self.idx_dev[B:2 * B]
         self.noise_seq = self.idx_dev[2 * B:].view(torch.int64)
+        # optional dropout after the dense layers (inert in the reference: default 0), keyed by the
+        # frames' global sequence numbers so that the masks do not depend on the GPU count
+        self.net.dropout_rate = float(dropout_rate)
+        self.net.dropout_seed = self.noise_seed + 0x5DEECE66D
+        self.net.dropout_keys = self.noise_seq
         self.use_graph = use_graph
         self._graphs = {}
         self._ring = torch.zeros(1024, 4, dtype=torch.float64).pin_memory()
@@ -275,7 +280,16 @@ class Reconstructor:
             self.out_host = [torch.zeros(2, B, plan.H, plan.W).pin_memory() for _ in range(n_out_slots)]
             self.out_dev = torch.zeros(2, B, plan.H, plan.W, device=dev)
         self._graphs = {}
-        self._seq = 0
+        self._sweep = -1           # index of the current train-mode sweep (keys the draws)
+        self._cloud = None
+
+    def begin_sweep(self):
+        """Start a new pass over the frames (every rank of a sharded sweep calls this once per
+        pass): new added-cloud draws and noise keys for train-mode inputs."""
+        self._sweep += 1
+        if self.train_mode_inputs:
+            seed = (int(self.noise_seed) * 1000003 + self._sweep) % (2 ** 32)
+            self._cloud = np.random.RandomState(seed).randint(0, self.cube.T, size=self.cube.T).astype(np.int32)
 
     def record_event(self):
         """Event after everything enqueued so far (the D2H copy of the last ``run_batch``)."""
@@ -327,13 +341,16 @@ class Reconstructor:
         h = self._idx_ring[islot]
         h[:n] = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.int32))
         if self.train_mode_inputs:
-            import random as _r
-            rnd = self.py_random or _r
+            # Reference quirk Q1: the "test" generator of reconstruct_gridded_nc adds clouds and
+            # jitter.  The cloud index and the noise key of a frame depend only on (seed, sweep
+            # number, ABSOLUTE frame number): every rank of a sharded sweep draws the same table, the
+            # result does not depend on the world size, and the global `random` is never touched.
             T = self.cube.T
-            h[B:B + n] = torch.tensor([rnd.randrange(0, T) for _ in range(n)], dtype=torch.int32)
-            seq = torch.arange(self._seq, self._seq + n, dtype=torch.int64)
-            h[2 * B:].view(torch.int64)[:n] = seq
-            self._seq += n
+            if self._cloud is None:
+                self.begin_sweep()
+            fr = np.asarray(frames, dtype=np.int64)
+            h[B:B + n] = torch.from_numpy(self._cloud[fr])
+            h[2 * B:].view(torch.int64)[:n] = torch.from_numpy(fr + self._sweep * T)
         self.idx_dev.copy_(h, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()

@@ -235,6 +235,19 @@ int dincae_dense_tc_bwd_data(const float* dz, int lddz, const void* w8, const fl
                              int N, float* dx, int lddx, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- dropout (optional; the reference's tf.layers.dropout is inert) -----------------
+ * dincae_dropout_fwd: y[b][n] <- y * keep / (1 - rate) in place, keep drawn from Philox4x32-10 keyed by
+ *   (seed, step, row key, n) with row key = row_keys[b] (device int64, e.g. the frame's sequence
+ *   number) or first_global_row + b when row_keys is NULL: independent of batch slot and GPU count.
+ *   `step` distinguishes the layers / calls that share a seed.  mask (may be NULL): keep mask, one
+ *   byte per element [B][N].
+ * Backward: dropout follows a ReLU, so the stored output is > 0 exactly where the unit was active
+ *   AND kept -- the ReLU gate of dincae_dense_bwd_data / conv3x3_dgrad already applies the mask; the
+ *   1 / (1 - rate) factor is dincae_scale_rows on that gradient. */
+int dincae_dropout_fwd(float* y, int B, int N, int ld, float rate, uint64_t seed, uint64_t step,
+                       int first_global_row, const int64_t* row_keys, uint8_t* mask, void* stream);
+int dincae_scale_rows(float* x, int B, int N, int ld, float factor, void* stream);
+
 /* ---- dense-bottleneck gradients in factored form (new capability) ------------------------------
  * The gradient of a dense kernel is dW = x^T dz (x [Bt,K]: the layer input, dz [Bt,N]: gradient of
  * its pre-activation, Bt frames of the GLOBAL batch).  These entry points let the optimiser work

@@ -57,6 +57,19 @@ def test_reconstruct_gridded_nc_all_options(small_example, tmp_path):
     assert np.array_equal(np.ma.getmaskarray(out["meandata"]), never)
     assert np.all(out["sigma_rec"].compressed() > 0)
     assert os.path.isfile(os.path.join(outdir, "model-001.ckpt.pt"))
+    # TensorBoard event file: the reference's scalars and images (DINCAE/__init__.py:575-584), one
+    # entry per optimisation step; 3 images per tag, flipped and masked, at the grid's size
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(os.path.join(outdir, "train"), size_guidance={"images": 0, "scalars": 0})
+    acc.Reload()
+    tags = acc.Tags()
+    assert set(tags["scalars"]) >= {"Validation/cost", "Validation/RMS"}
+    assert [ev.step for ev in acc.Scalars("Validation/cost")] == list(range(12))
+    assert abs(acc.Scalars("Validation/cost")[-1].value - loss[-1]) < 1e-6 * max(1.0, abs(loss[-1]))
+    for name in ("m_rec", "m_true", "sigma2_rec"):
+        for j in range(3):
+            evs = acc.Images("Validation/%s/image/%d" % (name, j))
+            assert len(evs) == 12 and evs[0].width == 48 and evs[0].height == 40
 
 
 def test_reconstruct_gridded_files_learns(small_example, tmp_path):
