@@ -19,6 +19,8 @@
 #include "umma.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dincae {
@@ -70,6 +72,7 @@ struct BfConvParams {
   uint4* g_prev;
   uint4* dx_hi;
   const uint4* dx_add;
+  long long* dbg;          // DINCAE_BF_DEBUG=1: role timeline of CTA 0 ([3][256][4] clock64 values)
 };
 
 struct BfParams {
@@ -139,6 +142,7 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
     const uint32_t w_bytes = (uint32_t)L.w_elems * 16u;
     int s = 0;
     uint32_t ph = 0;
+    int dbg_n = 0;
     for (int tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x) {
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
       const int rbi = rem / L.tiles_x, tx = rem - rbi * L.tiles_x;
@@ -192,7 +196,10 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
             }
           }
         }
+        long long t_a = 0, t_b = 0;
+        if (P.dbg) t_a = clock64();
         mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (P.dbg) t_b = clock64();
         if (warp == 0) {
           if (elect_one()) {
             mbar_expect_tx(&full_bar[s], w_bytes + plane_bytes * ((via_tma[0] ? 1u : 0u) + (via_tma[1] ? 1u : 0u)));
@@ -229,6 +236,10 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (P.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && dbg_n < 256) {
+          long long* d = P.dbg + 4 * dbg_n++;
+          d[0] = t_a; d[1] = t_b; d[2] = clock64(); d[3] = tile;
+        }
         if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
@@ -243,11 +254,15 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
     int lt = 0;
     for (int tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
+      long long t_a = 0, t_b = 0, t_c = 0;
+      if (P.dbg) t_a = clock64();
       mbar_wait(&tempty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      if (P.dbg) t_b = clock64();
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(buf * L.acc_cols);
       for (int ch = 0; ch < L.n_chunks; ++ch) {
         mbar_wait(&full_bar[s], ph);
+        if (P.dbg && ch == 0) t_c = clock64();
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = (smem_u32(ring + (size_t)s * L.stage_elems) >> 4);
@@ -267,6 +282,10 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      if (P.dbg && blockIdx.x == 0 && lane == 0 && lt < 256) {
+        long long* d = P.dbg + 1024 + 4 * lt;
+        d[0] = t_a; d[1] = t_b; d[2] = t_c; d[3] = clock64();
       }
     }
   } else {
@@ -300,7 +319,10 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
         o_half = (b * P.c_lo * Hh + (y >> 1)) * Wh + (xt >> 1);
         o_hi = (b * P.c_hi * P.H + y) * P.W + xt;
       }
+      long long t_a = 0, t_b = 0;
+      if (P.dbg) t_a = clock64();
       mbar_wait(&tfull_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      if (P.dbg) t_b = clock64();
       tc_fence_after();
       // work units = (M-tile j, pair of output planes), dealt round-robin to the warps of a quadrant
       const int npair = (P.out_planes + 1) >> 1;
@@ -420,6 +442,10 @@ conv3x3_bf16_kernel(const BfParams Q, const __grid_constant__ CUtensorMap tm0,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (P.dbg && blockIdx.x == 0 && warp == BF_EPI_WARP0 && lane == 0 && lt < 256) {
+        long long* d = P.dbg + 2048 + 4 * lt;
+        d[0] = t_a; d[1] = t_b; d[2] = clock64(); d[3] = tile;
+      }
     }
   }
   tc_fence_before();
@@ -526,6 +552,18 @@ static int launch_conv_bf16(int mode, int srcm, BfConvParams& P, cudaStream_t st
     }
   }
   Q.m.tma_only = (srcm == 0 && Q.m.tma0 && (P.p1 == 0 || Q.m.tma1)) ? 1 : 0;
+  static long long* dbg_dev = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("DINCAE_BF_DEBUG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg_dev, 3072 * sizeof(long long));
+  }
+  P.dbg = nullptr;
+  if (dbg_on) {
+    cudaMemsetAsync(dbg_dev, 0, 3072 * sizeof(long long), st);
+    P.dbg = dbg_dev;
+  }
   Q.c = P;
   const size_t smem = (size_t)Q.m.n_stages * Q.m.stage_elems * 16 + 128;
   if (!attr_set[which]) {
@@ -543,6 +581,19 @@ static int launch_conv_bf16(int mode, int srcm, BfConvParams& P, cudaStream_t st
     launch_k(conv3x3_bf16_kernel<1, 0>, grid, BF_THREADS, smem, st, Q, tm0, tm1);
   else
     launch_k(conv3x3_bf16_kernel<1, 1>, grid, BF_THREADS, smem, st, Q, tm0, tm1);
+  if (dbg_on) {
+    static long long h[3072];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "conv_bf16 timeline CTA0: mode=%d srcm=%d Xb=%d N=%d chunks=%d stages=%d tiles=%d tma_only=%d\n", mode,
+            srcm, Q.m.Xb, Q.m.Nmma, Q.m.n_chunks, Q.m.n_stages, Q.m.n_tiles, Q.m.tma_only);
+    const long long t0 = h[1024];
+    for (int i = 2; i < 10 && h[1024 + 4 * i]; ++i)
+      fprintf(stderr, "  tile %2d mma: wait_tempty %7lld..%7lld first_full %7lld issued %7lld | epi: wait_tfull %7lld..%7lld done %7lld | load(chunk %d): wait_empty %7lld..%7lld arrived %7lld\n",
+              i, h[1024 + 4 * i] - t0, h[1024 + 4 * i + 1] - t0, h[1024 + 4 * i + 2] - t0, h[1024 + 4 * i + 3] - t0,
+              h[2048 + 4 * i] - t0, h[2048 + 4 * i + 1] - t0, h[2048 + 4 * i + 2] - t0, Q.m.n_chunks * i,
+              h[4 * Q.m.n_chunks * i] - t0, h[4 * Q.m.n_chunks * i + 1] - t0, h[4 * Q.m.n_chunks * i + 2] - t0);
+  }
   return check_launch();
 }
 

@@ -17,6 +17,7 @@
 #include "bf16.cuh"
 #include "umma.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace dincae {
 
@@ -267,6 +268,275 @@ __global__ void __launch_bounds__(256, 2) adam_factored_kernel(float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same update with the rank-Bt product on the tensor cores (mma.sync m16n8k8, TF32 operands,
+// fp32 accumulation): data parallel, Bt = world x B frames enter every weight's gradient, and the
+// FFMA kernel above turns FMA-bound (128 FMAs per weight at 8 x 16 frames: 6.1 ms per configs[3]
+// kernel against 1.9 ms at Bt = 16).  CTA = 16 rows x 256 columns, 8 warps x (16 x 32): per 8
+// frames a warp issues 4 MMAs for 12 shared-memory loads.  In the bf16 network the factors are
+// bf16 values, which TF32 holds exactly, so the products are exact; fp32 factors are truncated to
+// TF32 by the tensor core (used only in the tf32 / bf16 precision modes).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int AM_XP = 20;      // padded row lengths of the staged factors (bank-conflict free fragments)
+constexpr int AM_ZP = 264;
+
+__global__ void __launch_bounds__(256, 2) adam_factored_mma_kernel(float* __restrict__ w, float* __restrict__ m,
+                                                                   float* __restrict__ v, int ldw, Factor fx,
+                                                                   Factor fz, int Bt, int rows_per_rank, int K, int N,
+                                                                   float grad_scale, const double* __restrict__ denom,
+                                                                   float beta1, float beta2, float eps,
+                                                                   const float* __restrict__ state,
+                                                                   uint32_t* __restrict__ w8) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float xs[16][AM_XP];
+  __shared__ __align__(16) float zs[16][AM_ZP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.y * 16, n0 = blockIdx.x * 256;
+  const int cw = 32 * warp;                                   // this warp's first column in the tile
+  // p, m, v of the thread's 2 rows x 4 n-tiles x 2 columns: requested before the factor loop
+  float2 pp[2][4], mm[2][4], vv[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + g + 8 * r, n = n0 + cw + 8 * j + 2 * t;
+      const bool ok = k < K && n < N;
+      const size_t at = (size_t)k * ldw + n;
+      pp[r][j] = ok ? *reinterpret_cast<const float2*>(w + at) : make_float2(0.f, 0.f);
+      mm[r][j] = ok ? *reinterpret_cast<const float2*>(m + at) : make_float2(0.f, 0.f);
+      vv[r][j] = ok ? *reinterpret_cast<const float2*>(v + at) : make_float2(0.f, 0.f);
+    }
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+  for (int b0 = 0; b0 < Bt; b0 += 16) {
+    if (tid < 64) {                                           // x chunk: 16 frames x 16 rows as float4
+      const int bb = tid >> 2, c = tid & 3;
+      const int k = k0 + 4 * c;
+      const bool ok = b0 + bb < Bt && k < K;
+      const float* row = ok ? factor_row(fx, b0 + bb, rows_per_rank) : fx.base;
+      *reinterpret_cast<float4*>(&xs[bb][4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + k), ok);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                             // dz chunk: 16 frames x 256 columns as float4
+      const int idx = tid + 256 * r;
+      const int bb = idx >> 6, c = idx & 63;
+      const int nn = n0 + 4 * c;
+      const bool ok = b0 + bb < Bt && nn < N;
+      const float* row = ok ? factor_row(fz, b0 + bb, rows_per_rank) : fz.base;
+      *reinterpret_cast<float4*>(&zs[bb][4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + nn), ok);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s8 = 0; s8 < 16; s8 += 8) {
+      // A = x^T: A[row][frame] = xs[frame][row]; fragment (g, t), (g+8, t), (g, t+4), (g+8, t+4)
+      const uint32_t a[4] = {__float_as_uint(xs[s8 + t][g]), __float_as_uint(xs[s8 + t][g + 8]),
+                             __float_as_uint(xs[s8 + t + 4][g]), __float_as_uint(xs[s8 + t + 4][g + 8])};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // B[frame][col] = zs[frame][col]; fragment (frame t, col g), (frame t+4, col g)
+        const uint32_t bq0 = __float_as_uint(zs[s8 + t][cw + 8 * j + g]);
+        const uint32_t bq1 = __float_as_uint(zs[s8 + t + 4][cw + 8 * j + g]);
+        mma_tf32_16x8x8(acc[j], a, bq0, bq1);
+      }
+    }
+    __syncthreads();
+  }
+  if (denom) grad_scale /= (float)(*denom);
+  const float gs = grad_scale * state[4];
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  uint32_t* stage = reinterpret_cast<uint32_t*>(&zs[0][0]);      // [2 kb][32 nb][8 rows][8 n] bf16 = 8 KB
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // accumulator fragment: c0, c1 = (row g, cols 2t, 2t+1); c2, c3 = (row g+8, same columns)
+      float pa[2] = {pp[r][j].x, pp[r][j].y}, ma[2] = {mm[r][j].x, mm[r][j].y}, va[2] = {vv[r][j].x, vv[r][j].y};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float gk = acc[j][2 * r + c] * gs;
+        ma[c] = ma[c] + (gk - ma[c]) * omb1;
+        va[c] = va[c] + (gk * gk - va[c]) * omb2;
+        pa[c] = pa[c] - (ma[c] * lr_t) / (sqrtf(va[c]) + eps);
+      }
+      const int row = g + 8 * r, col = cw + 8 * j + 2 * t;
+      const int k = k0 + row, n = n0 + col;
+      if (k < K && n < N) {
+        const size_t at = (size_t)k * ldw + n;
+        *reinterpret_cast<float2*>(w + at) = make_float2(pa[0], pa[1]);
+        *reinterpret_cast<float2*>(m + at) = make_float2(ma[0], ma[1]);
+        *reinterpret_cast<float2*>(v + at) = make_float2(va[0], va[1]);
+      }
+      if (w8) stage[((row >> 3) * 32 + (col >> 3)) * 32 + (row & 7) * 4 + ((col & 7) >> 1)] = bf2_pack(pa[0], pa[1]);
+    }
+  if (w8) {
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(&zs[0][0]);
+    const int NB = N >> 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = tid + 256 * r;                   // 16-byte unit: kb * 256 + nb * 8 + row
+      const int kb = idx >> 8, nb = (idx >> 3) & 31, row = idx & 7;
+      const int k = k0 + 8 * kb + row, nn = n0 + 8 * nb;
+      if (k < K && nn < N)
+        reinterpret_cast<uint4*>(w8)[((size_t)(k >> 3) * NB + (nn >> 3)) * 8 + row] = src[idx];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for 16 < Bt <= 128: a CTA owns a block of 256 columns, stages dz[:, block]
+// ONCE (Bt x 256 floats in shared memory) and walks down its share of the rows; per 16-row tile
+// only the x tile (Bt x 16) is new, and it is prefetched into registers during the previous
+// tile together with the tile's p, m, v.  (The per-tile staging of the kernel above re-read the dz
+// block for every 16 rows -- 139 KB of factors per 106 KB of weight traffic at Bt = 128 -- with one
+// exposed load latency per 16 frames: 6.3 ms per configs[3] kernel, no faster than FFMA.)
+// ---------------------------------------------------------------------------------------------
+constexpr int AP_MAX_BT = 128;
+
+__global__ void __launch_bounds__(256, 1) adam_factored_persist_kernel(float* __restrict__ w, float* __restrict__ m,
+                                                                       float* __restrict__ v, int ldw, Factor fx,
+                                                                       Factor fz, int Bt, int rows_per_rank, int K,
+                                                                       int N, int tiles_per_cta, float grad_scale,
+                                                                       const double* __restrict__ denom, float beta1,
+                                                                       float beta2, float eps,
+                                                                       const float* __restrict__ state,
+                                                                       uint32_t* __restrict__ w8) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float ap_smem[];
+  const int Bp = (Bt + 7) & ~7;
+  float* zs = ap_smem;                                  // [Bp][AM_ZP]
+  float* xs0 = zs + (size_t)Bp * AM_ZP;                 // [2][Bp][AM_XP]
+  uint32_t* stage = reinterpret_cast<uint32_t*>(xs0 + 2 * (size_t)Bp * AM_XP);     // 8 KB
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 256;
+  const int cw = 32 * warp;
+  const int n_tiles = (K + 15) >> 4;
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  int tile1 = tile0 + tiles_per_cta;
+  if (tile1 > n_tiles) tile1 = n_tiles;
+  // ---- dz block, once ----------------------------------------------------------------------------
+  for (int idx = tid; idx < Bp * 64; idx += 256) {
+    const int bb = idx >> 6, c = idx & 63;
+    const int nn = n0 + 4 * c;
+    const bool ok = bb < Bt && nn < N;
+    const float* row = ok ? factor_row(fz, bb, rows_per_rank) : fz.base;
+    *reinterpret_cast<float4*>(&zs[(size_t)bb * AM_ZP + 4 * c]) = ldg_f4_pred(reinterpret_cast<const float4*>(row + nn), ok);
+  }
+  // x tile loader: element e = tid + 256 * u  ->  frame e / 4, float4 column e % 4
+  auto load_x = [&](int tile, float4 (&xr)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + 256 * u;
+      const int bb = e >> 2, c = e & 3;
+      const int k = 16 * tile + 4 * c;
+      const bool ok = bb < Bt && k < K && tile < tile1;
+      const float* row = ok ? factor_row(fx, bb, rows_per_rank) : fx.base;
+      xr[u] = ldg_f4_pred(reinterpret_cast<const float4*>(row + k), ok);
+    }
+  };
+  auto store_x = [&](int buf, const float4 (&xr)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + 256 * u;
+      const int bb = e >> 2, c = e & 3;
+      if (bb < Bp) *reinterpret_cast<float4*>(&xs0[((size_t)buf * Bp + bb) * AM_XP + 4 * c]) = xr[u];
+    }
+  };
+  float gscale = grad_scale;
+  if (denom) gscale /= (float)(*denom);
+  const float gs = gscale * state[4];
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  float4 xr[2];
+  load_x(tile0, xr);
+  store_x(0, xr);
+  __syncthreads();
+  int buf = 0;
+  for (int tile = tile0; tile < tile1; ++tile, buf ^= 1) {
+    const int k0 = 16 * tile;
+    float2 pp[2][4], mm[2][4], vv[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + g + 8 * r, n = n0 + cw + 8 * j + 2 * t;
+        const bool ok = k < K && n < N;
+        const size_t at = (size_t)k * ldw + n;
+        pp[r][j] = ok ? *reinterpret_cast<const float2*>(w + at) : make_float2(0.f, 0.f);
+        mm[r][j] = ok ? *reinterpret_cast<const float2*>(m + at) : make_float2(0.f, 0.f);
+        vv[r][j] = ok ? *reinterpret_cast<const float2*>(v + at) : make_float2(0.f, 0.f);
+      }
+    load_x(tile + 1, xr);                                  // next tile's x: in flight during the MMAs
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    const float* xs = xs0 + (size_t)buf * Bp * AM_XP;
+    for (int s8 = 0; s8 < Bp; s8 += 8) {
+      const uint32_t a[4] = {__float_as_uint(xs[(s8 + t) * AM_XP + g]), __float_as_uint(xs[(s8 + t) * AM_XP + g + 8]),
+                             __float_as_uint(xs[(s8 + t + 4) * AM_XP + g]),
+                             __float_as_uint(xs[(s8 + t + 4) * AM_XP + g + 8])};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t bq0 = __float_as_uint(zs[(size_t)(s8 + t) * AM_ZP + cw + 8 * j + g]);
+        const uint32_t bq1 = __float_as_uint(zs[(size_t)(s8 + t + 4) * AM_ZP + cw + 8 * j + g]);
+        mma_tf32_16x8x8(acc[j], a, bq0, bq1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float pa[2] = {pp[r][j].x, pp[r][j].y}, ma[2] = {mm[r][j].x, mm[r][j].y}, va[2] = {vv[r][j].x, vv[r][j].y};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float gk = acc[j][2 * r + c] * gs;
+          ma[c] = ma[c] + (gk - ma[c]) * omb1;
+          va[c] = va[c] + (gk * gk - va[c]) * omb2;
+          pa[c] = pa[c] - (ma[c] * lr_t) / (sqrtf(va[c]) + eps);
+        }
+        const int row = g + 8 * r, col = cw + 8 * j + 2 * t;
+        const int k = k0 + row, n = n0 + col;
+        if (k < K && n < N) {
+          const size_t at = (size_t)k * ldw + n;
+          *reinterpret_cast<float2*>(w + at) = make_float2(pa[0], pa[1]);
+          *reinterpret_cast<float2*>(m + at) = make_float2(ma[0], ma[1]);
+          *reinterpret_cast<float2*>(v + at) = make_float2(va[0], va[1]);
+        }
+        if (w8) stage[((row >> 3) * 32 + (col >> 3)) * 32 + (row & 7) * 4 + ((col & 7) >> 1)] = bf2_pack(pa[0], pa[1]);
+      }
+    store_x(buf ^ 1, xr);
+    __syncthreads();                                       // next x tile and the staged bf16 tile are complete
+    if (w8) {
+      const uint4* src = reinterpret_cast<const uint4*>(stage);
+      const int NB = N >> 3;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int idx = tid + 256 * r;
+        const int kb = idx >> 8, nb = (idx >> 3) & 31, row = idx & 7;
+        const int k = k0 + 8 * kb + row, nn = n0 + 8 * nb;
+        if (k < K && nn < N)
+          reinterpret_cast<uint4*>(w8)[((size_t)(k >> 3) * NB + (nn >> 3)) * 8 + row] = src[idx];
+      }
+      __syncthreads();                                     // the stage buffer is free again
+    }
+  }
+}
+
 // dw = x^T dz written out (tests / callers that want the matrix): the same tiling without Adam
 __global__ void __launch_bounds__(256) factored_expand_kernel(float* __restrict__ dw, int ldw, Factor fx, Factor fz,
                                                               int Bt, int rows_per_rank, int K, int N) {
@@ -485,9 +755,50 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
       (((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)x | (uintptr_t)dz) & 15))
     return DINCAE_EINVAL;
   Factor fx = {x, x_rank_stride, ldx}, fz = {dz, dz_rank_stride, lddz};
-  launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v, ldw,
-           fx, fz, world * rows_per_rank, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
-           reinterpret_cast<uint2*>(w8));
+  // Bt > 16 frames: the rank-Bt product goes to the tensor cores (TF32 operands; exact for the bf16
+  // network's factors).  DINCAE_ADAM_MMA=0 / 1 forces the FFMA / the tensor-core kernel.
+  static int force = -2;
+  if (force == -2) {
+    const char* e = getenv("DINCAE_ADAM_MMA");
+    force = e ? atoi(e) : -1;
+  }
+  const int Bt = world * rows_per_rank;
+  const bool use_mma = force == 1 || (force != 0 && Bt > 16);
+  // measured per configs[3] kernel (B200): Bt 32: 2.8 ms per-tile staging vs 3.0-3.8 persistent;
+  // Bt 64: 4.05 vs 3.3-4.0; Bt 128: 6.3 vs 3.9-4.7
+  if (use_mma && Bt > 48 && Bt <= AP_MAX_BT) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count <= 0) sm_count = 148;
+    }
+    const int Bp = (Bt + 7) & ~7;
+    const size_t smem = ((size_t)Bp * AM_ZP + 2 * (size_t)Bp * AM_XP) * sizeof(float) + 8192;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(adam_factored_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(((size_t)AP_MAX_BT * AM_ZP + 2 * (size_t)AP_MAX_BT * AM_XP) * sizeof(float) + 8192));
+      if (e != cudaSuccess) return cuda_rc(e);
+      attr_set = true;
+    }
+    const int col_blocks = ceil_div(N, 256), n_tiles = ceil_div(K, 16);
+    int row_splits = ceil_div(2 * sm_count, col_blocks);          // about two waves of CTAs
+    if (row_splits > n_tiles) row_splits = n_tiles;
+    const int tiles_per_cta = ceil_div(n_tiles, row_splits);
+    row_splits = ceil_div(n_tiles, tiles_per_cta);
+    launch_k(adam_factored_persist_kernel, dim3(col_blocks, row_splits), 256, smem, (cudaStream_t)stream, w, m, v, ldw,
+             fx, fz, Bt, rows_per_rank, K, N, tiles_per_cta, grad_scale, denom, beta1, beta2, eps, state,
+             reinterpret_cast<uint32_t*>(w8));
+  } else if (use_mma)
+    launch_k(adam_factored_mma_kernel, dim3(ceil_div(N, 256), ceil_div(K, 16)), 256, 0, (cudaStream_t)stream, w, m, v,
+             ldw, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
+             reinterpret_cast<uint32_t*>(w8));
+  else
+    launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v,
+             ldw, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
+             reinterpret_cast<uint2*>(w8));
   return check_launch();
 }
 

@@ -147,6 +147,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+// 16 lanes x 16 columns (tcgen05.ld.16x256b.x2): thread t of the warp receives, for lane a = t / 4
+// and column pair c = 2 * (t % 4):  v[0..1] = (lane a, cols c, c+1), v[2..3] = (lane a+8, same cols),
+// v[4..5] = (lane a, cols c+8, c+9), v[6..7] = (lane a+8, cols c+8, c+9).  `taddr` carries the first
+// of the 16 lanes (a multiple of 16 inside the warp's quadrant).
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile(

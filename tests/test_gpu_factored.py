@@ -24,7 +24,9 @@ def test_factor_ops_match_the_materialised_gradient(world, rows, K, N):
     g = torch.Generator().manual_seed(world * 100 + rows)
     pad = 64                                            # per-rank blobs with unrelated data in between
     stride = rows * K + rows * N + 2 * pad
-    blob = torch.randn(world, stride, generator=g).cuda()
+    # bf16-representable factors (what the bf16 network produces): the tensor-core variant of the
+    # Adam kernel (more than 16 frames) multiplies TF32 operands, which hold bf16 values exactly
+    blob = torch.randn(world, stride, generator=g).to(torch.bfloat16).float().cuda()
     xs = [blob[r, pad: pad + rows * K].view(rows, K) for r in range(world)]
     zs = [blob[r, 2 * pad + rows * K: 2 * pad + rows * K + rows * N].view(rows, N) for r in range(world)]
     x, dz = torch.cat(xs).double(), torch.cat(zs).double()
