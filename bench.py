@@ -390,6 +390,9 @@ def config_d_leg(a, world, rank, dist, barrier):
             "conv_tensor_frac": conv_fl / (conv_ms * 1e-3) / 1e12 / pk_tf, "tensor_peak_tflops": pk_tf,
             "tensor_peak_source": pk_tf_src,
             "tensor_pipe_ncu": "profiles/r2_configD_ncu.md (sm__pipe_tensor_cycles_active per kernel)"}
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        t = json.load(open(tp)).get(top[0]) if os.path.isfile(tp) else None
+        out["roofline"]["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"] if t else None
         out["kernel_breakdown_ms"] = {k: round(v[0], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
         out["conv_tflops_by_kernel"] = {k: round(v[2] / (v[0] * 1e-3) / 1e12, 1)
                                         for k, v in sorted(conv.items(), key=lambda kv: -kv[1][0])}
