@@ -16,6 +16,8 @@
 // all-gathered buffer is used in place.
 #include "bf16.cuh"
 #include "umma.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -537,6 +539,219 @@ __global__ void __launch_bounds__(256, 1) adam_factored_persist_kernel(float* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The single-GPU update (Bt <= 16) as a TMA pipeline.  adam_factored_kernel above keeps p, m, v
+// of a tile in registers between the load and the store, so a CTA has no bytes in flight while it
+// computes and the kernel tops out at 4.4-4.9 TB/s (67-75 % of the measured copy bandwidth).
+// Here one persistent CTA per SM walks a contiguous range of 16 x 256 tiles in ROW-MAJOR order
+// (along the columns of a 16-row block, then the next block: every CTA is a contiguous stream
+// through w, m and v -- walking down a column block instead touches 1 KB segments 33 KB apart and
+// measured 2.5 TB/s):
+//   * thread 0 keeps the p / m / v tiles of the NEXT TWO tiles in flight (3 stages x 48 KB,
+//     cp.async.bulk.tensor loads on an mbarrier per stage; out-of-range rows / columns are
+//     zero-filled by the tensor map and clipped again by the store);
+//   * the 512 threads form the gradient tile from the factors while those loads fly -- the x
+//     values of a thread's two rows stay in REGISTERS for the whole row block (32 registers;
+//     the CTA has the SM to itself), the 16 x 256 dz chunk of the next tile arrives one tile
+//     ahead by cp.async into a double-buffered 16 KB array;
+//   * p, m, v are updated in place in shared memory and leave through cp.async.bulk.tensor stores,
+//     the tiled bf16 copy through two 4 KB bulk copies; a stage is refilled only after the
+//     store that read it has finished reading (cp.async.bulk.wait_group.read).
+// Measured at configs[3] (43008 x 8296 / 8296 x 43008, 16 frames): 1.58 / 1.50 ms = 5.9 / 6.2 TB/s
+// (90 / 94 % of the 6.55 TB/s copy peak; the same pipeline with the arithmetic removed: 5.7 / 6.2)
+// against 2.09 / 1.93 ms for adam_factored_kernel.  256 threads x 4 rows: 4.4 TB/s (issue bound),
+// 1024 x 1: 4.9-5.2 TB/s; L2 evict-first hints on the loads / stores: no change.
+// Summation order and the m / v updates are those of adam_factored_kernel (bit-identical m, v);
+// the weight step uses the approximate sqrt / division below.
+// ---------------------------------------------------------------------------------------------
+constexpr int AT_STAGES = 3;
+constexpr int AT_TILE = 16 * 256;                                   // floats of one array's tile
+constexpr int AT_OFF_W8 = AT_STAGES * 3 * AT_TILE * 4;               // 2 x 8 KB bf16 staging
+constexpr int AT_OFF_ZS = AT_OFF_W8 + 2 * 8192;                      // 2 x [16][256] floats
+constexpr int AT_OFF_BAR = AT_OFF_ZS + 2 * AT_TILE * 4;
+constexpr int AT_SMEM = AT_OFF_BAR + 64 + 128;                       // + alignment slack
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+               :: "r"(smem_u32(dst_smem)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+
+// MUFU.SQRT / MUFU.RCP forms (relative error 2^-23 and 2 ulp): the IEEE sqrtf and division of the
+// other Adam kernels cost ~30 instructions per weight with slow-path branches and made this
+// kernel issue bound (measured 5.4 TB/s against 5.7-6.1 TB/s with the arithmetic removed); the
+// step lr * m / (sqrt(v) + eps) changes by < 4e-7 of itself, below one ulp of the weight.
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int AT_ROWS = 2;                                          // rows of the tile per thread
+constexpr int AT_THREADS = 64 * (16 / AT_ROWS);
+
+__global__ void __launch_bounds__(AT_THREADS, 1) adam_factored_tma_kernel(
+    const __grid_constant__ CUtensorMap tmw, const __grid_constant__ CUtensorMap tmm,
+    const __grid_constant__ CUtensorMap tmv, Factor fx, Factor fz, int Bt, int rows_per_rank, int K, int N,
+    float grad_scale, const double* __restrict__ denom, float beta1, float beta2, float eps,
+    const float* __restrict__ state, uint4* __restrict__ w8) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ unsigned char at_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(at_raw) + 127) & ~(uintptr_t)127);
+  float* tiles = reinterpret_cast<float*>(base);
+  uint2* w8s = reinterpret_cast<uint2*>(base + AT_OFF_W8);
+  float* zs = reinterpret_cast<float*>(base + AT_OFF_ZS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + AT_OFF_BAR);
+  const int tid = threadIdx.x, tn = tid & 63, tk = tid >> 6;
+  const int RT = (K + 15) >> 4, CB = (N + 255) >> 8, NB = N >> 3;
+  const long long T = (long long)RT * CB;
+  const long long t0 = T * blockIdx.x / gridDim.x, t1 = T * (blockIdx.x + 1) / gridDim.x;
+  if (t0 >= t1) return;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < AT_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_load = [&](long long t, int s) {                          // thread 0
+    const int rt = (int)(t / CB), cb = (int)(t - (long long)rt * CB);
+    float* dst = tiles + (size_t)s * 3 * AT_TILE;
+    mbar_expect_tx(&full[s], 3 * AT_TILE * 4);
+    tma_load_2d(dst, &tmw, cb * 256, rt * 16, &full[s]);
+    tma_load_2d(dst + AT_TILE, &tmm, cb * 256, rt * 16, &full[s]);
+    tma_load_2d(dst + 2 * AT_TILE, &tmv, cb * 256, rt * 16, &full[s]);
+    mbar_arrive(&full[s]);
+  };
+  if (tid == 0) {
+    issue_load(t0, 0);
+    if (t0 + 1 < t1) issue_load(t0 + 1, 1);
+  }
+  // dz chunk of a tile: 16 frames x 256 columns, four 16-byte cp.async per thread (zero fill
+  // outside the batch / the matrix)
+  auto fetch_z = [&](int cb, int buf, bool valid) {
+#pragma unroll
+    for (int r = 0; r < 1024 / AT_THREADS; ++r) {
+      const int idx = tid + AT_THREADS * r;
+      const int bb = idx >> 6, c = idx & 63;
+      const int nn = cb * 256 + 4 * c;
+      const bool ok = valid && bb < Bt && nn < N;
+      const float* row = ok ? factor_row(fz, bb, rows_per_rank) + nn : fz.base;
+      cp_async16_zfill(zs + buf * AT_TILE + bb * 256 + 4 * c, row, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float gscale = grad_scale;
+  if (denom) gscale /= (float)(*denom);
+  const float gs = gscale * state[4];                 // 1/n normalisation times the clip scale
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  int rt = (int)(t0 / CB), cb = (int)(t0 - (long long)rt * CB);
+  fetch_z(cb, 0, true);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  float x[16][AT_ROWS];
+  int x_rt = -1;
+  int i = 0;
+  for (long long t = t0; t < t1; ++t, ++i) {
+    const int s = i % AT_STAGES;
+    const uint32_t ph = (uint32_t)(i / AT_STAGES) & 1u;
+    const int n0 = cb * 256, k0 = rt * 16;
+    int rt_n = rt, cb_n = cb + 1;
+    if (cb_n == CB) { cb_n = 0; ++rt_n; }
+    fetch_z(cb_n, (i + 1) & 1, t + 1 < t1);            // next tile's dz chunk: lands during this tile
+    if (rt != x_rt) {                                  // x of this thread's rows, all frames
+      const int k = k0 + AT_ROWS * tk;
+#pragma unroll
+      for (int bb = 0; bb < 16; ++bb) {
+        const bool ok = bb < Bt && k < K;                // K is a multiple of 4: the AT_ROWS rows are in or out together
+        const float* row = ok ? factor_row(fx, bb, rows_per_rank) : fx.base;
+#pragma unroll
+        for (int r = 0; r < AT_ROWS; ++r) x[bb][r] = ok ? __ldg(row + k + r) : 0.f;
+      }
+      x_rt = rt;
+    }
+    float4 acc[AT_ROWS];
+#pragma unroll
+    for (int r = 0; r < AT_ROWS; ++r) acc[r] = f4_zero();
+    const float* zcur = zs + (i & 1) * AT_TILE;
+#pragma unroll
+    for (int bb = 0; bb < 16; ++bb) {
+      const float4 zv = *reinterpret_cast<const float4*>(&zcur[bb * 256 + 4 * tn]);
+#pragma unroll
+      for (int r = 0; r < AT_ROWS; ++r) acc[r] = f4_fma(x[bb][r], zv, acc[r]);
+    }
+    mbar_wait(&full[s], ph);
+    float* tw = tiles + (size_t)s * 3 * AT_TILE;
+    uint2* wst = w8s + (i & 1) * 1024;
+#pragma unroll
+    for (int r = 0; r < AT_ROWS; ++r) {
+      const int row = AT_ROWS * tk + r, at = row * 256 + 4 * tn;
+      const float4 p4 = *reinterpret_cast<const float4*>(tw + at);
+      const float4 m4 = *reinterpret_cast<const float4*>(tw + AT_TILE + at);
+      const float4 v4 = *reinterpret_cast<const float4*>(tw + 2 * AT_TILE + at);
+      float pa[4] = {p4.x, p4.y, p4.z, p4.w}, ma[4] = {m4.x, m4.y, m4.z, m4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float ga[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float gk = ga[c] * gs;
+        ma[c] = ma[c] + (gk - ma[c]) * omb1;
+        va[c] = va[c] + (gk * gk - va[c]) * omb2;
+        pa[c] = pa[c] - __fdividef(ma[c] * lr_t, sqrt_approx(va[c]) + eps);
+      }
+      *reinterpret_cast<float4*>(tw + at) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+      *reinterpret_cast<float4*>(tw + AT_TILE + at) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+      *reinterpret_cast<float4*>(tw + 2 * AT_TILE + at) = make_float4(va[0], va[1], va[2], va[3]);
+      if (w8)                                          // [kb][nb][8 rows][8 columns] bf16
+        wst[((row >> 3) * 32 + (tn >> 1)) * 16 + (row & 7) * 2 + (tn & 1)] =
+            make_uint2(bf2_pack(pa[0], pa[1]), bf2_pack(pa[2], pa[3]));
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // next dz chunk
+    fence_async_smem();                                // the updated tiles become visible to the TMA engine
+    if (tid == 0) bulk_wait_read<0>();                 // the previous tile's stores have left shared memory
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_2d(&tmw, n0, k0, tw);
+      tma_store_2d(&tmm, n0, k0, tw + AT_TILE);
+      tma_store_2d(&tmv, n0, k0, tw + 2 * AT_TILE);
+      if (w8) {
+        const int nbs = min(32, NB - (n0 >> 3));
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          if (k0 + 8 * kb < K)
+            bulk_s2g(w8 + ((size_t)((k0 >> 3) + kb) * NB + (n0 >> 3)) * 8, wst + kb * 512, (uint32_t)nbs * 128u);
+      }
+      bulk_commit();
+      if (t + 2 < t1) issue_load(t + 2, (i + 2) % AT_STAGES);
+    }
+    cb = cb_n;
+    rt = rt_n;
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
+static int at_encode_map(CUtensorMap* tm, const float* base, int K, int N, int ldw) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return DINCAE_ECUDA;
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)K};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldw * 4};
+  const cuuint32_t box[2] = {256, 16};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = (int)r;
+    return DINCAE_ECUDA;
+  }
+  return DINCAE_OK;
+}
+
 // dw = x^T dz written out (tests / callers that want the matrix): the same tiling without Adam
 __global__ void __launch_bounds__(256) factored_expand_kernel(float* __restrict__ dw, int ldw, Factor fx, Factor fz,
                                                               int Bt, int rows_per_rank, int K, int N) {
@@ -795,10 +1010,34 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
     launch_k(adam_factored_mma_kernel, dim3(ceil_div(N, 256), ceil_div(K, 16)), 256, 0, (cudaStream_t)stream, w, m, v,
              ldw, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
              reinterpret_cast<uint32_t*>(w8));
-  else
-    launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v,
-             ldw, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
-             reinterpret_cast<uint2*>(w8));
+  else {
+    // Bt <= 16: the TMA pipeline (DINCAE_ADAM_TMA=0 selects the register-staged kernel)
+    const char* e_tma = getenv("DINCAE_ADAM_TMA");       // read per call: the tests switch between the two
+    const bool use_tma = e_tma ? atoi(e_tma) != 0 : true;
+    if (use_tma && Bt <= 16) {
+      static int sm_count = 0;
+      static bool attr_set = false;
+      if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+        cudaError_t e = cudaFuncSetAttribute(adam_factored_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+        if (e != cudaSuccess) return cuda_rc(e);
+        attr_set = true;
+      }
+      CUtensorMap tmw, tmm, tmv;
+      int rc = at_encode_map(&tmw, w, K, N, ldw);
+      if (!rc) rc = at_encode_map(&tmm, m, K, N, ldw);
+      if (!rc) rc = at_encode_map(&tmv, v, K, N, ldw);
+      if (rc) return rc;
+      launch_k(adam_factored_tma_kernel, sm_count, AT_THREADS, AT_SMEM, (cudaStream_t)stream, tmw, tmm, tmv, fx, fz, Bt,
+               rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state, reinterpret_cast<uint4*>(w8));
+    } else
+      launch_k(adam_factored_kernel, dim3(ceil_div(N, 256), ceil_div(K, AF_TK)), 256, 0, (cudaStream_t)stream, w, m, v,
+               ldw, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state,
+               reinterpret_cast<uint2*>(w8));
+  }
   return check_launch();
 }
 

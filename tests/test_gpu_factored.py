@@ -162,3 +162,41 @@ def test_factored_adam_keeps_the_tiled_bf16_copy_current(rows, K, N):
     check(lib.dincae_dense_tc_tile_weights(ptr(w), N, K, N, ptr(ref8), stream()))
     torch.cuda.synchronize()
     assert torch.equal(w8, ref8)
+
+
+@pytest.mark.parametrize("rows,K,N,with_w8", [(5, 40, 24, False), (16, 136, 72, True), (7, 2648, 536, True),
+                                              (16, 536, 2648, True), (12, 8296, 1032, True), (3, 20, 300, False)])
+def test_tma_pipelined_adam_equals_the_register_staged_kernel(rows, K, N, with_w8, monkeypatch):
+    """adam_factored_tma_kernel (persistent CTAs, TMA loads / stores, 3 stages) against
+    adam_factored_kernel on the same inputs: same summation order -> bit-identical m, v; weights
+    within the approximate-division bound; bf16 tile copy consistent with the weights; ragged row / column tiles, tile ranges that cross column blocks,
+    fewer tiles than CTAs; two consecutive steps so that the second starts from non-trivial m, v."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(rows * 7 + K)
+    x = torch.randn(rows, K, generator=g).cuda()
+    dz = torch.randn(rows, N, generator=g).cuda()
+    w0 = torch.randn(K, N, generator=g).cuda()
+    state = torch.tensor([0.9, 0.999, 0.0, 1e-2, 0.8, 0, 0, 0], dtype=torch.float32, device="cuda")
+    denom = torch.tensor([3.0], dtype=torch.float64, device="cuda")
+    out = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DINCAE_ADAM_TMA", mode)
+        w, m, v = w0.clone(), torch.zeros(K, N, device="cuda"), torch.zeros(K, N, device="cuda")
+        w8 = torch.zeros(K * N, dtype=torch.bfloat16, device="cuda") if with_w8 else None
+        for _ in range(2):
+            check(lib.dincae_adam_update_factored(ptr(w), ptr(m), ptr(v), N, ptr(x), rows * K, K, ptr(dz), rows * N, N,
+                                                  1, rows, K, N, 1.0, ptr(denom), 0.9, 0.999, 1e-8, ptr(state),
+                                                  ptr(w8) if with_w8 else None, stream()))
+        torch.cuda.synchronize()
+        out.append((w, m, v, w8))
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])      # m, v
+    # the weight step of the TMA kernel uses MUFU sqrt / reciprocal: < 4e-7 of a step of <= 2 lr
+    # (i.e. a last-bit rounding difference of the weight at most)
+    assert bool(((out[0][0] - out[1][0]).abs() <= 2.4e-7 * out[0][0].abs().clamp(min=1.0)).all())
+    assert not torch.equal(out[0][0], w0)
+    if with_w8:                                            # each copy is the bf16 tile form of its own weights
+        for w, _, _, w8 in out:
+            ref8 = torch.zeros_like(w8)
+            check(lib.dincae_dense_tc_tile_weights(ptr(w), N, K, N, ptr(ref8), stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(w8, ref8)

@@ -1,5 +1,6 @@
 """Stand-alone timing of the dense-bottleneck kernels at BASELINE configs[3] sizes (K = 43008,
 N = 8296): python tools/dense_bench.py [B] [world]"""
+import os
 import sys
 
 import torch
@@ -52,11 +53,14 @@ for (k, n) in ((K, N), (N, K)):
     w8 = torch.zeros(k * n, dtype=torch.bfloat16, device="cuda")
     state = torch.tensor([0.9, 0.999, 0.0, 1e-3, 1.0, 0, 0, 0], dtype=torch.float32, device="cuda")
     ss = torch.zeros(1, dtype=torch.float64, device="cuda")
-    ms = timeit(lambda: check(lib.dincae_adam_update_factored(
-        ptr(w), ptr(m), ptr(v), n, ptr(xf), B * k, k, ptr(zf), B * n, n, world, B, k, n, 1.0, None, 0.9, 0.999,
-        1e-8, ptr(state), ptr(w8), st)))
-    print("adam_factored  Bt=%d %dx%d  %7.3f ms  %6.0f GB/s (26 B/param incl. bf16 copy)" % (world * B, k, n, ms, 26.0 * k * n / ms / 1e6),
-          flush=True)
+    for tma in ("0", "1"):
+        os.environ["DINCAE_ADAM_TMA"] = tma                 # register-staged kernel / TMA pipeline (Bt <= 16)
+        ms = timeit(lambda: check(lib.dincae_adam_update_factored(
+            ptr(w), ptr(m), ptr(v), n, ptr(xf), B * k, k, ptr(zf), B * n, n, world, B, k, n, 1.0, None, 0.9, 0.999,
+            1e-8, ptr(state), ptr(w8), st)))
+        print("adam_factored  Bt=%d %dx%d  DINCAE_ADAM_TMA=%s %7.3f ms  %6.0f GB/s (26 B/param incl. bf16 copy)" %
+              (world * B, k, n, tma, ms, 26.0 * k * n / ms / 1e6), flush=True)
+    del os.environ["DINCAE_ADAM_TMA"]
     ms = timeit(lambda: check(lib.dincae_dense_factored_sumsq(
         ptr(xf), B * k, k, ptr(zf), B * n, n, world, B, k, n, ptr(ss), ptr(ws), ws_b, st)))
     print("gram sumsq     Bt=%d %dx%d  %7.3f ms" % (world * B, k, n, ms), flush=True)
