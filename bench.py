@@ -285,8 +285,8 @@ def traced_step(trainer, B, jitter, reps):
         # back and the events measure execution, not the python launch gaps
         torch.cuda._sleep(8_000_000)
         ebb0.record()
-        trainer.cube.build_batch(trainer.frame_idx, trainer.cloud_idx, B, net.X[0], net.xtrue,
-                                 net.n_noncloud, jitter_std=jitter, seed=1, noise_seq=trainer.noise_seq)
+        net.build_input(trainer.cube, trainer.frame_idx, trainer.cloud_idx, B, jitter_std=jitter, seed=1,
+                        noise_seq=trainer.noise_seq)
         ebb1.record()
         net.forward(B)
         net.loss_backward(B, False, normalise=False)

@@ -26,6 +26,9 @@ SIGNATURES = {
     "dincae_build_batch": (c_int, [vp, vp, vp, vp, vp, vp, vp, POINTER(c_double), POINTER(c_double),
                                    c_int, c_int, c_int, c_int, c_int, vp, vp, c_int, vp, c_uint64,
                                    vp, vp, c_int, vp, vp, vp]),
+    "dincae_build_batch_p8": (c_int, [vp, vp, vp, vp, vp, vp, vp, POINTER(c_double), POINTER(c_double),
+                                      c_int, c_int, c_int, c_int, c_int, vp, vp, c_int, vp, c_uint64,
+                                      vp, vp, c_int, vp, c_int, vp, vp, vp]),
     "dincae_set_conv_backend": (c_int, [c_int]),
     "dincae_get_conv_backend": (c_int, []),
     "dincae_conv3x3_fwd": (c_int, [vp, c_int, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int,

@@ -1,6 +1,7 @@
 // Input pipeline on the device: temporal-mean removal and the per-batch channel stacking,
 // added-cloud masking and jitter of DINCAE/__init__.py:155-227.  HBM-bound gather kernels.
 #include "common.cuh"
+#include "bf16.cuh"
 #include "philox.cuh"
 
 namespace dincae {
@@ -96,13 +97,25 @@ __global__ void __launch_bounds__(256) cube_anom_kernel(const float* __restrict_
   }
 }
 
+// Box-Muller on the MUFU units (lg2 / sqrt / sin / cos approximations, absolute error ~1e-6):
+// the values are noise, and the IEEE logf / sqrtf / sincospif made the batch builder issue bound
+// (~230 instructions per variable and pixel: 0.52 ms per 16-frame batch at configs[3]).
+__device__ __forceinline__ float bm_radius(uint32_t a) {
+  const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1]
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+  return r;
+}
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
-  const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * logf(u1));
+  const float r = bm_radius(a);
+  const float th = ((float)b + 0.5f) * (6.283185307179586f * 2.3283064365386963e-10f);
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(th, &s, &c);
   return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ float box_muller_cos(uint32_t a, uint32_t b) {
+  const float th = ((float)b + 0.5f) * (6.283185307179586f * 2.3283064365386963e-10f);
+  return bm_radius(a) * __cosf(th);
 }
 
 #define DINCAE_MAX_NDATA 8
@@ -119,11 +132,14 @@ struct BatchParams {
   const int32_t* cloud_idx;
   const double* noise;
   const int64_t* noise_seq;
-  float* xin;
+  float* xin;              // P4 fp32 output (may be null when xin8 is set)
+  uint4* xin8;             // P8 bf16 output [B][planes8][H][W][8] (bf16 network), or null
   float* xtrue;
   int32_t* n_noncloud;
   uint64_t seed;
-  int ndata, T, H, W, ntime_win, B, nvar_planes;
+  int ndata, T, H, W, ntime_win, B, nvar_planes, planes8;
+  unsigned jitter_mask;    // bit j: jitter[j] != 0
+  float jitter_f[DINCAE_MAX_NDATA];
   int round_tf32;          // network inputs rounded to TF32 (tensor-core conv back end)
   float inv_var[DINCAE_MAX_NDATA];
   double jitter[DINCAE_MAX_NDATA];
@@ -160,10 +176,11 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
 
     // jitter slots per variable j: channels 2j, 2j+2nd+4, 2j+4nd+4 (reference quirk Q4)
     uint4 rnd = make_uint4(0, 0, 0, 0);
-    float gauss[4] = {0.f, 0.f, 0.f, 0.f};
+    float gauss[3] = {0.f, 0.f, 0.f};
     int gauss_j = -1;
 
     float lane[4];
+    float pair[8];
 #pragma unroll(ND ? NPL : 1)
     for (int plane = 0; plane < n_planes; ++plane) {
 #pragma unroll
@@ -199,18 +216,17 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
                 if (P.noise != nullptr) {
                   const double z = P.noise[((size_t)b * 3 * nd + 3 * j + slot) * HW + p];
                   v = (float)((double)v + P.jitter[j] * z);
-                } else if (P.jitter[j] != 0.0) {
+                } else if ((P.jitter_mask >> j) & 1u) {
                   if (gauss_j != j) {
                     const uint64_t seq = P.noise_seq ? (uint64_t)P.noise_seq[b] : (uint64_t)i;
                     rnd = philox4x32_10(
                         make_uint4((uint32_t)p, (uint32_t)j, (uint32_t)seq, (uint32_t)(seq >> 32)),
                         make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
                     const float2 g0 = box_muller(rnd.x, rnd.y);
-                    const float2 g1 = box_muller(rnd.z, rnd.w);
-                    gauss[0] = g0.x; gauss[1] = g0.y; gauss[2] = g1.x; gauss[3] = g1.y;
+                    gauss[0] = g0.x; gauss[1] = g0.y; gauss[2] = box_muller_cos(rnd.z, rnd.w);
                     gauss_j = j;
                   }
-                  v = fmaf((float)P.jitter[j], gauss[slot], v);
+                  v = fmaf(P.jitter_f[j], gauss[slot], v);
                 }
               }
             } else {
@@ -222,8 +238,19 @@ __global__ void __launch_bounds__(256) build_batch_kernel(const BatchParams P) {
       }
       float4 out = make_float4(lane[0], lane[1], lane[2], lane[3]);
       if (P.round_tf32) out = to_tf32(out);
-      reinterpret_cast<float4*>(P.xin)[((size_t)(b * P.nvar_planes + plane) * P.H + y) * P.W + x] = out;
+      if (P.xin) reinterpret_cast<float4*>(P.xin)[((size_t)(b * P.nvar_planes + plane) * P.H + y) * P.W + x] = out;
+      if (P.xin8) {                                      // two P4 planes -> one P8 plane (same bits as p4_to_p8)
+        const int h = plane & 1;
+        pair[4 * h] = out.x; pair[4 * h + 1] = out.y; pair[4 * h + 2] = out.z; pair[4 * h + 3] = out.w;
+        if (h == 1 || plane == n_planes - 1) {
+          if (h == 0) { pair[4] = 0.f; pair[5] = 0.f; pair[6] = 0.f; pair[7] = 0.f; }
+          P.xin8[((size_t)(b * P.planes8 + (plane >> 1)) * P.H + y) * P.W + x] = bf8_pack(pair);
+        }
+      }
     }
+    if (P.xin8)                                          // planes beyond the stacked channels stay zero
+      for (int q = (n_planes + 1) >> 1; q < P.planes8; ++q)
+        P.xin8[((size_t)(b * P.planes8 + q) * P.H + y) * P.W + x] = make_uint4(0u, 0u, 0u, 0u);
     // target: un-perturbed channels 0 and 1 of the current frame (:227)
     {
       const size_t at = (size_t)i * HW + p;
@@ -270,7 +297,7 @@ extern "C" int dincae_prepare_cube(const float* data, const uint8_t* missing, in
   return check_launch();
 }
 
-extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
+static int build_batch_impl(const float* anom, const uint8_t* missing,
                                   const uint8_t* cloud_missing,
                                   const float* lon_scaled, const float* lat_scaled,
                                   const float* doy_cos, const float* doy_sin,
@@ -278,11 +305,12 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
                                   int ndata, int T, int H, int W, int ntime_win,
                                   const int32_t* frame_idx, const int32_t* cloud_idx, int B,
                                   const double* noise, uint64_t seed, const int64_t* noise_seq,
-                                  float* xin, int nvar_planes, float* xtrue,
+                                  float* xin, int nvar_planes, void* xin8, int planes8, float* xtrue,
                                   int32_t* n_noncloud, void* stream) {
   if (!anom || !missing || !lon_scaled || !lat_scaled || !doy_cos || !doy_sin || !inv_var_host ||
-      !frame_idx || !xin || !xtrue || !n_noncloud)
+      !frame_idx || (!xin && !xin8) || !xtrue || !n_noncloud)
     return DINCAE_EINVAL;
+  if (xin8 && 2 * planes8 < nvar_planes) return DINCAE_EINVAL;
   if (ndata <= 0 || ndata > DINCAE_MAX_NDATA || T <= 0 || H <= 0 || W <= 0 || B <= 0 ||
       ntime_win < 1 || (ntime_win & 1) == 0)
     return DINCAE_EINVAL;
@@ -293,6 +321,7 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   P.anom = anom; P.missing = missing; P.cloud_missing = cloud_missing ? cloud_missing : missing; P.lon_scaled = lon_scaled; P.lat_scaled = lat_scaled;
   P.doy_cos = doy_cos; P.doy_sin = doy_sin; P.frame_idx = frame_idx; P.cloud_idx = cloud_idx;
   P.noise = noise; P.noise_seq = noise_seq; P.xin = xin; P.xtrue = xtrue;
+  P.xin8 = reinterpret_cast<uint4*>(xin8); P.planes8 = planes8; P.jitter_mask = 0;
   P.n_noncloud = n_noncloud; P.seed = seed;
   P.ndata = ndata; P.T = T; P.H = H; P.W = W; P.ntime_win = ntime_win; P.B = B;
   P.nvar_planes = nvar_planes;
@@ -300,6 +329,8 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   for (int j = 0; j < DINCAE_MAX_NDATA; ++j) {
     P.inv_var[j] = j < ndata ? (float)inv_var_host[j] : 0.f;
     P.jitter[j] = (j < ndata && jitter_std_host) ? jitter_std_host[j] : 0.0;
+    P.jitter_f[j] = (float)P.jitter[j];
+    if (P.jitter[j] != 0.0) P.jitter_mask |= 1u << j;
   }
   const long long total = (long long)B * H * W;
   const int threads = 256;
@@ -315,4 +346,40 @@ extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
   else
     launch_k(build_batch_kernel<0, 0>, blocks, threads, 0, (cudaStream_t)stream, P);
   return check_launch();
+}
+
+extern "C" int dincae_build_batch(const float* anom, const uint8_t* missing,
+                                  const uint8_t* cloud_missing,
+                                  const float* lon_scaled, const float* lat_scaled,
+                                  const float* doy_cos, const float* doy_sin,
+                                  const double* inv_var_host, const double* jitter_std_host,
+                                  int ndata, int T, int H, int W, int ntime_win,
+                                  const int32_t* frame_idx, const int32_t* cloud_idx, int B,
+                                  const double* noise, uint64_t seed, const int64_t* noise_seq,
+                                  float* xin, int nvar_planes, float* xtrue,
+                                  int32_t* n_noncloud, void* stream) {
+  if (!xin) return DINCAE_EINVAL;
+  return build_batch_impl(anom, missing, cloud_missing, lon_scaled, lat_scaled, doy_cos, doy_sin, inv_var_host,
+                          jitter_std_host, ndata, T, H, W, ntime_win, frame_idx, cloud_idx, B, noise, seed,
+                          noise_seq, xin, nvar_planes, nullptr, 0, xtrue, n_noncloud, stream);
+}
+
+// The same batch written as bf16 P8 planes [B][planes8][H][W][8] for the bf16 network (bit-identical
+// to dincae_build_batch followed by dincae_p4_to_p8; `xin` may be null, then only the bf16 copy is
+// produced -- saves the fp32 write and the conversion pass: 0.7 GB of traffic per 16 frames of
+// configs[3]).
+extern "C" int dincae_build_batch_p8(const float* anom, const uint8_t* missing,
+                                     const uint8_t* cloud_missing,
+                                     const float* lon_scaled, const float* lat_scaled,
+                                     const float* doy_cos, const float* doy_sin,
+                                     const double* inv_var_host, const double* jitter_std_host,
+                                     int ndata, int T, int H, int W, int ntime_win,
+                                     const int32_t* frame_idx, const int32_t* cloud_idx, int B,
+                                     const double* noise, uint64_t seed, const int64_t* noise_seq,
+                                     float* xin, int nvar_planes, void* xin8, int planes8, float* xtrue,
+                                     int32_t* n_noncloud, void* stream) {
+  if (!xin8 || planes8 <= 0) return DINCAE_EINVAL;
+  return build_batch_impl(anom, missing, cloud_missing, lon_scaled, lat_scaled, doy_cos, doy_sin, inv_var_host,
+                          jitter_std_host, ndata, T, H, W, ntime_win, frame_idx, cloud_idx, B, noise, seed,
+                          noise_seq, xin, nvar_planes, xin8, planes8, xtrue, n_noncloud, stream);
 }

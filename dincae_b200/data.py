@@ -114,16 +114,27 @@ class DeviceCube:
         return self.anom.numel() * 4 + self.missing.numel()
 
     def build_batch(self, frame_idx, cloud_idx, B, xin, xtrue, n_noncloud, jitter_std=None,
-                    noise=None, seed=0, noise_seq=None):
+                    noise=None, seed=0, noise_seq=None, xin8=None, planes8=0):
         """Fill ``xin`` (P4), ``xtrue`` and add to ``n_noncloud`` for frames
         ``frame_idx[:B]`` (device int32).  ``cloud_idx is None`` = test mode (no added clouds,
-        no jitter); otherwise ``jitter_std`` (one value per variable) scales the noise."""
+        no jitter); otherwise ``jitter_std`` (one value per variable) scales the noise.
+        ``xin8`` (bf16 P8, ``planes8`` planes): the bf16 network's input written directly;
+        ``xin`` may then be None."""
         key = tuple(float(j) for j in (jitter_std if jitter_std is not None else [0.0] * self.ndata))
         if len(key) != self.ndata:
             raise ValueError("jitter_std needs one entry per variable")
         jit = self._jitter_cache.get(key)
         if jit is None:
             jit = self._jitter_cache[key] = _lib.doubles(key)
+        if xin8 is not None:
+            check(self.lib.dincae_build_batch_p8(
+                ptr(self.anom), ptr(self.missing), ptr(self.cloud_missing), ptr(self.lon_scaled),
+                ptr(self.lat_scaled), ptr(self.doy_cos), ptr(self.doy_sin), self._inv_var_c, jit,
+                self.ndata, self.T, self.H, self.W, self.ntime_win,
+                ptr(frame_idx), ptr(cloud_idx), B, ptr(noise), int(seed) & (2 ** 64 - 1),
+                ptr(noise_seq), ptr(xin), self.nvar_planes, ptr(xin8), planes8, ptr(xtrue), ptr(n_noncloud),
+                stream_ptr()), "build_batch_p8")
+            return
         check(self.lib.dincae_build_batch(
             ptr(self.anom), ptr(self.missing), ptr(self.cloud_missing), ptr(self.lon_scaled), ptr(self.lat_scaled),
             ptr(self.doy_cos), ptr(self.doy_sin), self._inv_var_c, jit,

@@ -459,6 +459,11 @@ class Network:
         return self._conv_names[self.plan.L + l - 1]
 
     # ---- forward --------------------------------------------------------------------------
+    def build_input(self, cube, frame_idx, cloud_idx, B, **kw):
+        """Stack the network input of frames ``frame_idx[:B]`` from the device cube
+        (``DeviceCube.build_batch``) into this network's input buffer."""
+        cube.build_batch(frame_idx, cloud_idx, B, self.X[0], self.xtrue, self.n_noncloud, **kw)
+
     def forward(self, B, save_signs=None):
         """Encoder -> dense -> decoder on self.X[0][:B]; leaves xrec in self.D[L]."""
         P, lib, st = self.plan, self.lib, stream_ptr()
@@ -702,6 +707,7 @@ class NetworkBF16(Network):
 
         # the batch builder writes planar-4 fp32 with exactly ceil(nvar/4) planes
         self.x0_planes = layout.planes(P.nvar)
+        self.input_p8 = False                 # True once build_input() fills X8[0] directly
         self.X = [torch.zeros(B, self.x0_planes, P.H, P.W, 4, **f32)]
         self.X8 = [torch.zeros(B, P.ep8[k], P.sizes[k][0], P.sizes[k][1], 8, **b16) for k in range(L + 1)]
         self.xtrue = torch.zeros(B, P.H, P.W, 2, **f32)
@@ -837,6 +843,13 @@ class NetworkBF16(Network):
                     ptr(w), e["cinp"], e["cout_pad"], d["ci_first"], d["nd"], None,
                     ptr(self.wbf[d["off"]:]), st), 6 * e["size"], 0)
 
+    def build_input(self, cube, frame_idx, cloud_idx, B, **kw):
+        """The batch builder writes the bf16 P8 input directly (dincae_build_batch_p8): no fp32
+        copy, no conversion pass.  ``forward`` then skips ``p4_to_p8(input)``."""
+        self.input_p8 = True
+        cube.build_batch(frame_idx, cloud_idx, B, None, self.xtrue, self.n_noncloud,
+                         xin8=self.X8[0], planes8=self.plan.ep8[0], **kw)
+
     # ---- forward ------------------------------------------------------------------------------------
     def forward(self, B, save_signs=None):
         P, st = self.plan, stream_ptr()
@@ -844,9 +857,10 @@ class NetworkBF16(Network):
         save_signs = self.train if save_signs is None else save_signs
         self.prepare_weights()
         h0, w0 = P.sizes[0]
-        self._call("p4_to_p8(input)", "dincae_p4_to_p8", (
-            ptr(self.X[0]), self.x0_planes, P.ep8[0], B, h0, w0, ptr(self.X8[0]), st),
-            6 * B * h0 * w0 * P.nvar, 0)
+        if not self.input_p8:                       # input supplied as fp32 P4 (host feed, tests)
+            self._call("p4_to_p8(input)", "dincae_p4_to_p8", (
+                ptr(self.X[0]), self.x0_planes, P.ep8[0], B, h0, w0, ptr(self.X8[0]), st),
+                6 * B * h0 * w0 * P.nvar, 0)
         for l in range(1, L + 1):
             h, w = P.sizes[l - 1]
             name = self._enc_name(l)

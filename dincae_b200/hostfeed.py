@@ -42,6 +42,8 @@ def _upload(net, frames_x, frames_t):
         # (tcgen05 would otherwise truncate the low 13 mantissa bits)
         x = ((x.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
     net.X[0][:n].copy_(x.view(n, P.H, P.W, planes, 4).permute(0, 3, 1, 2, 4))
+    if getattr(net, "input_p8", False):
+        net.input_p8 = False                      # the bf16 network converts X[0] itself
     net.xtrue[:n].copy_(t)
     return n
 

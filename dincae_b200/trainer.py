@@ -88,9 +88,8 @@ class Trainer:
         net, B = self.net, self.B
         if 1 in phases:
             net.n_noncloud.zero_()
-            self.cube.build_batch(self.frame_idx, self.cloud_idx, B, net.X[0], net.xtrue,
-                                  net.n_noncloud, jitter_std=self.jitter_std, seed=self.noise_seed,
-                                  noise_seq=self.noise_seq)
+            net.build_input(self.cube, self.frame_idx, self.cloud_idx, B, jitter_std=self.jitter_std,
+                            seed=self.noise_seed, noise_seq=self.noise_seq)
             net.forward(B)
             net.loss_backward(B, self.truth_uncertain, normalise=False, phase=1)
         if 2 in phases:
@@ -301,8 +300,8 @@ class Reconstructor:
         net, B = self.net, self.B
         net.n_noncloud.zero_()
         cloud = self.idx_dev[B:2 * B] if self.train_mode_inputs else None
-        self.cube.build_batch(self.idx_dev[:B], cloud, n, net.X[0], net.xtrue, net.n_noncloud,
-                              jitter_std=self.jitter_std, seed=self.noise_seed, noise_seq=self.idx_dev[2 * B:].view(torch.int64))
+        net.build_input(self.cube, self.idx_dev[:B], cloud, n, jitter_std=self.jitter_std,
+                        seed=self.noise_seed, noise_seq=self.idx_dev[2 * B:].view(torch.int64))
         net.forward(n, save_signs=False)
         if self.records:
             net.head_recon_records(n, self._mean_dev, self._never_dev, self._fill, self._mean_is_f32,

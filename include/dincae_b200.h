@@ -87,6 +87,21 @@ int dincae_build_batch(const float* anom, const uint8_t* missing,
                        float* xin, int nvar_planes, float* xtrue, int32_t* n_noncloud,
                        void* stream);
 
+/* The same batch for the bf16 network: xin8 = bf16 P8 planes [B][planes8][H][W][8] of the stacked
+ * channels (bit-identical to dincae_build_batch followed by dincae_p4_to_p8; planes beyond the
+ * stacked channels are zero).  xin (fp32 P4) may be NULL -- then only the bf16 copy is written.
+ * Replaces the same reference lines as dincae_build_batch. */
+int dincae_build_batch_p8(const float* anom, const uint8_t* missing,
+                          const uint8_t* cloud_missing,
+                          const float* lon_scaled, const float* lat_scaled,
+                          const float* doy_cos, const float* doy_sin,
+                          const double* inv_var_host, const double* jitter_std_host,
+                          int ndata, int T, int H, int W, int ntime_win,
+                          const int32_t* frame_idx, const int32_t* cloud_idx, int B,
+                          const double* noise, uint64_t seed, const int64_t* noise_seq,
+                          float* xin, int nvar_planes, void* xin8, int planes8, float* xtrue,
+                          int32_t* n_noncloud, void* stream);
+
 /* ---- 3x3 convolutions -------------------------------------------------------------- */
 
 /* Which kernels dincae_conv3x3_fwd / _dgrad / _wgrad launch: 1 (default) = tcgen05 kind::tf32

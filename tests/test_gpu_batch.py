@@ -195,3 +195,44 @@ def test_tensor_core_backend_rounds_inputs():
     assert np.array_equal(rounded[0], tf32_round(exact[0]))
     assert np.array_equal(rounded[1], exact[1])
     assert rounded[2] == exact[2]
+
+
+@pytest.mark.parametrize("nf,win,backend", [(4, 3, 1), (1, 3, 1), (2, 3, 0), (1, 5, 1)])
+def test_bf16_p8_output_equals_fp32_build_plus_conversion(nf, win, backend):
+    """dincae_build_batch_p8 (the bf16 network's input written directly, with or without the fp32
+    copy) == dincae_build_batch followed by dincae_p4_to_p8, bit for bit -- explicit noise and the
+    Philox path, compile-time and run-time channel decode, planes beyond the stacked channels zero."""
+    from dincae_b200 import _lib, layout
+    from dincae_b200._lib import check, ptr
+    from dincae_b200.data import DeviceCube
+    lib = _lib.load()
+    lib.dincae_set_conv_backend(backend)
+    rs = np.random.RandomState(nf + win)
+    T, H, W, B = 6, 12, 20, 5
+    lon, lat, time, fields = random_cube(rs, T, H, W, nf)
+    missing = [np.ma.getmaskarray(f) for f in fields]
+    cube = DeviceCube(lon, lat, time, fields, missing, list(rs.uniform(0.5, 2.0, nf)), win)
+    frames = dev(rs.randint(0, T, size=B).astype(np.int32))
+    clouds = dev(rs.randint(0, T, size=B).astype(np.int32))
+    seq = dev(np.arange(B, dtype=np.int64) + 40)
+    planes8 = layout.planes8(cube.nvar) + 1                 # one spare plane: must come back zero
+    for noise in (dev(rs.standard_normal((B, 3 * nf, H, W))), None):
+        kw = dict(jitter_std=[0.1] * nf, noise=noise, seed=5, noise_seq=seq)
+        xin = torch.zeros(B, cube.nvar_planes, H, W, 4, device="cuda")
+        xtrue = torch.zeros(B, H, W, 2, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        cube.build_batch(frames, clouds, B, xin, xtrue, cnt, **kw)
+        want8 = torch.full((B, planes8, H, W, 8), 7.0, dtype=torch.bfloat16, device="cuda")
+        check(lib.dincae_p4_to_p8(ptr(xin), cube.nvar_planes, planes8, B, H, W, ptr(want8),
+                                  torch.cuda.current_stream().cuda_stream))
+        for with_f32 in (True, False):
+            xin2 = torch.zeros_like(xin) if with_f32 else None
+            got8 = torch.full_like(want8, 3.0)
+            xtrue2, cnt2 = torch.zeros_like(xtrue), torch.zeros_like(cnt)
+            cube.build_batch(frames, clouds, B, xin2, xtrue2, cnt2, xin8=got8, planes8=planes8, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(got8.view(torch.int16), want8.view(torch.int16))
+            assert torch.equal(xtrue2, xtrue) and int(cnt2.item()) == int(cnt.item())
+            if with_f32:
+                assert torch.equal(xin2, xin)
+        assert float(want8.float().abs().max()) > 0 and float(want8[:, -1].float().abs().max()) == 0
