@@ -752,6 +752,279 @@ static int at_encode_map(CUtensorMap* tm, const float* base, int K, int N, int l
   return DINCAE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The data-parallel update (16 < Bt <= 128 frames) on the same TMA pipeline, gradient tile by
+// mma.sync (TF32, as adam_factored_mma_kernel).  Differences to the kernel above:
+//   * the dz operand of Bt frames x 256 columns does not fit next to the p / m / v stages, so the
+//     walk is DOWN a column block and each thread keeps its B fragments (dz of the warp's 16
+//     columns, all frames: 4 Bt/8 registers) for the whole task; the 16 x Bt x-chunk of the next
+//     tile arrives by cp.async.  To keep DRAM pages open the tasks (row range, column block) are
+//     dealt column block fastest over the CTAs, so the CTAs of a wave walk down adjacent column
+//     blocks of the same rows in step;
+//   * accumulator fragments own (row g / g+8, columns 2t, 2t+1): on a row-major tile those are
+//     8-way bank conflicts, so the p / m / v tiles travel as eight 16 x 32 boxes with the 128-byte
+//     TMA swizzle (16-byte chunk ^= row % 8), which makes the float2 accesses conflict free;
+//   * a 17th warp issues the 48 tensor-map loads / stores per tile (the compute warps hand a
+//     finished stage over through an mbarrier), w8 staging is per stage.
+// ---------------------------------------------------------------------------------------------
+constexpr int AX_XP = 20;                                 // padded frame pitch of the x chunk (floats)
+constexpr int AX_CWARPS = 16;
+constexpr int AX_THREADS = 32 * AX_CWARPS + 32;
+constexpr int AX_OFF_W8 = AT_STAGES * 3 * AT_TILE * 4;     // 3 x 8 KB bf16 staging (one per stage)
+constexpr int AX_OFF_XS = AX_OFF_W8 + AT_STAGES * 8192;
+__host__ __device__ constexpr int ax_smem_bytes(int nk) { return AX_OFF_XS + 2 * nk * 8 * AX_XP * 4 + 64 + 1024; }
+
+struct AxWalk {                                            // this CTA's tile sequence
+  int CB, RT, TPS, ntasks, G;
+  int task, cb, rt, rt1;
+  __device__ void start(int cta) { task = cta - G; rt = 0; rt1 = 0; next(); }
+  __device__ bool valid() const { return task < ntasks; }
+  __device__ void next() {
+    if (++rt < rt1) return;
+    task += G;
+    if (task >= ntasks) return;
+    const int rs = task / CB;
+    cb = task - rs * CB;
+    rt = rs * TPS;
+    rt1 = min(RT, rt + TPS);
+  }
+};
+
+template <int NK>
+__global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
+    const __grid_constant__ CUtensorMap tmw, const __grid_constant__ CUtensorMap tmm,
+    const __grid_constant__ CUtensorMap tmv, Factor fx, Factor fz, int Bt, int rows_per_rank, int K, int N, int RS,
+    float grad_scale, const double* __restrict__ denom, float beta1, float beta2, float eps,
+    const float* __restrict__ state, uint4* __restrict__ w8) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ unsigned char ax_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ax_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int BP = NK * 8;
+  float* xs = reinterpret_cast<float*>(base + AX_OFF_XS);                  // [2][BP][AX_XP]
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + AX_OFF_XS + 2 * BP * AX_XP * 4);
+  uint64_t* done = full + AT_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  AxWalk wk;
+  wk.CB = (N + 255) >> 8; wk.RT = (K + 15) >> 4; wk.TPS = (wk.RT + RS - 1) / RS;
+  wk.ntasks = wk.CB * RS; wk.G = gridDim.x;
+  const int NB = N >> 3;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], AX_CWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == AX_CWARPS) {
+    // ---------------- TMA warp: loads two tiles ahead, stores behind ---------------------------
+    if (lane != 0) return;
+    auto issue_load = [&](const AxWalk& a, int s) {
+      const int n0 = a.cb * 256, k0 = a.rt * 16;
+      const int nbox = min(8, (N - n0 + 31) >> 5);
+      unsigned char* dst = base + (size_t)s * 3 * AT_TILE * 4;
+      mbar_expect_tx(&full[s], (uint32_t)(3 * nbox * 2048));
+      for (int b = 0; b < nbox; ++b) {
+        tma_load_2d(dst + b * 2048, &tmw, n0 + 32 * b, k0, &full[s]);
+        tma_load_2d(dst + AT_TILE * 4 + b * 2048, &tmm, n0 + 32 * b, k0, &full[s]);
+        tma_load_2d(dst + 2 * AT_TILE * 4 + b * 2048, &tmv, n0 + 32 * b, k0, &full[s]);
+      }
+      mbar_arrive(&full[s]);
+    };
+    AxWalk ld = wk, st = wk;
+    ld.start(blockIdx.x);
+    st.start(blockIdx.x);
+    for (int q = 0; q < 2 && ld.valid(); ++q) { issue_load(ld, q); ld.next(); }
+    for (int i = 0; st.valid(); ++i) {
+      const int s = i % AT_STAGES;
+      mbar_wait(&done[s], (uint32_t)(i / AT_STAGES) & 1u);
+      const int n0 = st.cb * 256, k0 = st.rt * 16;
+      const int nbox = min(8, (N - n0 + 31) >> 5);
+      const unsigned char* src = base + (size_t)s * 3 * AT_TILE * 4;
+      for (int b = 0; b < nbox; ++b) {
+        tma_store_2d(&tmw, n0 + 32 * b, k0, src + b * 2048);
+        tma_store_2d(&tmm, n0 + 32 * b, k0, src + AT_TILE * 4 + b * 2048);
+        tma_store_2d(&tmv, n0 + 32 * b, k0, src + 2 * AT_TILE * 4 + b * 2048);
+      }
+      if (w8) {
+        const int nbs = min(32, NB - (n0 >> 3));
+        const unsigned char* wsrc = base + AX_OFF_W8 + s * 8192;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          if (k0 + 8 * kb < K)
+            bulk_s2g(w8 + ((size_t)((k0 >> 3) + kb) * NB + (n0 >> 3)) * 8, wsrc + kb * 4096, (uint32_t)nbs * 128u);
+      }
+      bulk_commit();
+      st.next();
+      if (ld.valid()) {
+        bulk_wait_read<1>();                           // the stage of tile i - 1 has been read out
+        issue_load(ld, (i + 2) % AT_STAGES);
+        ld.next();
+      }
+    }
+    bulk_wait<0>();
+    return;
+  }
+
+  // ---------------- compute warps ------------------------------------------------------------------
+  const int g = lane >> 2, t = lane & 3;
+  const int cw = 16 * warp;                                   // this warp's first column in the tile
+  float gscale = grad_scale;
+  if (denom) gscale /= (float)(*denom);
+  const float gs = gscale * state[4];
+  const float lr_t = state[3];
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  // x chunk of a tile: BP frames x 16 rows, one 16-byte cp.async per thread (zero fill outside)
+  auto fetch_x = [&](int rt, int buf, bool valid) {
+    if (tid < BP * 4) {
+      const int bb = tid >> 2, c = tid & 3;
+      const int k = 16 * rt + 4 * c;
+      const bool ok = valid && bb < Bt && k < K;
+      const float* src = ok ? factor_row(fx, bb, rows_per_rank) + k : fx.base;
+      cp_async16_zfill(xs + ((size_t)buf * BP + bb) * AX_XP + 4 * c, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  AxWalk it = wk;
+  it.start(blockIdx.x);
+  if (!it.valid()) return;
+  fetch_x(it.rt, 0, true);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  named_bar_sync(1, 32 * AX_CWARPS);
+  uint32_t bfr[NK][2][2];
+  int cur_task = -1;
+  // swizzled position of this thread's float2 in a 16 x 256 tile (eight 16 x 32 boxes of 2 KB,
+  // 128-byte rows, 16-byte chunk index ^= row % 8): rows g and g + 8, n-tiles j = 0, 1
+  int toff[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int chunk = 4 * (warp & 1) + 2 * j + (t >> 1);
+    toff[j] = (warp >> 1) * 2048 + g * 128 + ((chunk ^ g) << 4) + (t & 1) * 8;
+  }
+  for (int i = 0; it.valid(); ++i) {
+    const int s = i % AT_STAGES;
+    if (it.task != cur_task) {                                // B fragments: dz of the warp's columns, all frames
+      const int n0 = it.cb * 256;
+#pragma unroll
+      for (int ks = 0; ks < NK; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int f = 8 * ks + t + 4 * h, col = n0 + cw + 8 * j + g;
+            const bool ok = f < Bt && col < N;
+            bfr[ks][j][h] = ok ? __float_as_uint(__ldg(factor_row(fz, f, rows_per_rank) + col)) : 0u;
+          }
+      cur_task = it.task;
+    }
+    AxWalk nx = it;
+    nx.next();
+    fetch_x(nx.rt, (i + 1) & 1, nx.valid());                  // next tile's x chunk: lands during this tile
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    const float* xc = xs + (size_t)(i & 1) * BP * AX_XP;
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+      // A = x^T: A[row][frame] = xc[frame][row]; fragment (g, t), (g+8, t), (g, t+4), (g+8, t+4)
+      const uint32_t a[4] = {__float_as_uint(xc[(8 * ks + t) * AX_XP + g]), __float_as_uint(xc[(8 * ks + t) * AX_XP + g + 8]),
+                             __float_as_uint(xc[(8 * ks + t + 4) * AX_XP + g]),
+                             __float_as_uint(xc[(8 * ks + t + 4) * AX_XP + g + 8])};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) mma_tf32_16x8x8(acc[j], a, bfr[ks][j][0], bfr[ks][j][1]);
+    }
+    mbar_wait(&full[s], (uint32_t)(i / AT_STAGES) & 1u);
+    unsigned char* tw = base + (size_t)s * 3 * AT_TILE * 4;
+    uint32_t* wst = reinterpret_cast<uint32_t*>(base + AX_OFF_W8 + s * 8192);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int at = toff[j] + r * 1024;                    // row g + 8 r: same swizzle phase
+        const float2 p2 = *reinterpret_cast<const float2*>(tw + at);
+        const float2 m2 = *reinterpret_cast<const float2*>(tw + AT_TILE * 4 + at);
+        const float2 v2 = *reinterpret_cast<const float2*>(tw + 2 * AT_TILE * 4 + at);
+        float pa[2] = {p2.x, p2.y}, ma[2] = {m2.x, m2.y}, va[2] = {v2.x, v2.y};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float gk = acc[j][2 * r + c] * gs;
+          ma[c] = ma[c] + (gk - ma[c]) * omb1;
+          va[c] = va[c] + (gk * gk - va[c]) * omb2;
+          pa[c] = pa[c] - __fdividef(ma[c] * lr_t, sqrt_approx(va[c]) + eps);
+        }
+        *reinterpret_cast<float2*>(tw + at) = make_float2(pa[0], pa[1]);
+        *reinterpret_cast<float2*>(tw + AT_TILE * 4 + at) = make_float2(ma[0], ma[1]);
+        *reinterpret_cast<float2*>(tw + 2 * AT_TILE * 4 + at) = make_float2(va[0], va[1]);
+        const int row = g + 8 * r, col = cw + 8 * j + 2 * t;
+        if (w8) wst[((row >> 3) * 32 + (col >> 3)) * 32 + (row & 7) * 4 + ((col & 7) >> 1)] = bf2_pack(pa[0], pa[1]);
+      }
+    asm volatile("cp.async.wait_all;" ::: "memory");          // next x chunk
+    fence_async_smem();                                        // updated tile visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
+    named_bar_sync(1, 32 * AX_CWARPS);                         // x double buffer
+    it = nx;
+  }
+}
+
+static int ax_encode_map(CUtensorMap* tm, const float* base, int K, int N, int ldw) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return DINCAE_ECUDA;
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)K};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldw * 4};
+  const cuuint32_t box[2] = {32, 16};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = (int)r;
+    return DINCAE_ECUDA;
+  }
+  return DINCAE_OK;
+}
+
+// row splits of the task grid: the smallest count whose waves are >= 96 % full (tasks are
+// column blocks x row splits, dealt round robin over the CTAs), at least 8 tiles per task
+static int ax_row_splits(int CB, int RT, int G) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int rs = 1; rs <= RT && rs <= 4096; ++rs) {
+    if ((RT + rs - 1) / rs < 8 && rs > 1) break;
+    const long long tasks = (long long)CB * rs;
+    const long long waves = (tasks + G - 1) / G;
+    const double eff = (double)tasks / (double)(waves * G);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = rs; }
+    if (eff >= 0.96) return rs;
+  }
+  return best;
+}
+
+template <int NK>
+static int ax_launch(int sm_count, const CUtensorMap& tmw, const CUtensorMap& tmm, const CUtensorMap& tmv, Factor fx,
+                     Factor fz, int Bt, int rows_per_rank, int K, int N, float grad_scale, const double* denom,
+                     float beta1, float beta2, float eps, const float* state, void* w8, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(adam_factored_tma_mma_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ax_smem_bytes(NK));
+    if (e != cudaSuccess) return cuda_rc(e);
+    attr_set = true;
+  }
+  const int RS = ax_row_splits(ceil_div(N, 256), ceil_div(K, 16), sm_count);
+  launch_k(adam_factored_tma_mma_kernel<NK>, sm_count, AX_THREADS, ax_smem_bytes(NK), st, tmw, tmm, tmv, fx, fz, Bt,
+           rows_per_rank, K, N, RS, grad_scale, denom, beta1, beta2, eps, state, reinterpret_cast<uint4*>(w8));
+  return DINCAE_OK;
+}
+
 // dw = x^T dz written out (tests / callers that want the matrix): the same tiling without Adam
 __global__ void __launch_bounds__(256) factored_expand_kernel(float* __restrict__ dw, int ldw, Factor fx, Factor fz,
                                                               int Bt, int rows_per_rank, int K, int N) {
@@ -981,7 +1254,30 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
   const bool use_mma = force == 1 || (force != 0 && Bt > 16);
   // measured per configs[3] kernel (B200): Bt 32: 2.8 ms per-tile staging vs 3.0-3.8 persistent;
   // Bt 64: 4.05 vs 3.3-4.0; Bt 128: 6.3 vs 3.9-4.7
-  if (use_mma && Bt > 48 && Bt <= AP_MAX_BT) {
+  const char* e_tma = getenv("DINCAE_ADAM_TMA");       // read per call: the tests switch between the kernels
+  const bool use_tma = e_tma ? atoi(e_tma) != 0 : true;
+  if (use_mma && use_tma && Bt <= 128) {
+    static int sm_count_x = 0;
+    if (!sm_count_x) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count_x, cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count_x <= 0) sm_count_x = 148;
+    }
+    CUtensorMap tmw, tmm, tmv;
+    int rc = ax_encode_map(&tmw, w, K, N, ldw);
+    if (!rc) rc = ax_encode_map(&tmm, m, K, N, ldw);
+    if (!rc) rc = ax_encode_map(&tmv, v, K, N, ldw);
+    if (rc) return rc;
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (Bt <= 32)
+      rc = ax_launch<4>(sm_count_x, tmw, tmm, tmv, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state, w8, st);
+    else if (Bt <= 64)
+      rc = ax_launch<8>(sm_count_x, tmw, tmm, tmv, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state, w8, st);
+    else
+      rc = ax_launch<16>(sm_count_x, tmw, tmm, tmv, fx, fz, Bt, rows_per_rank, K, N, grad_scale, denom, beta1, beta2, eps, state, w8, st);
+    if (rc) return rc;
+  } else if (use_mma && Bt > 48 && Bt <= AP_MAX_BT) {
     static int sm_count = 0;
     if (!sm_count) {
       int dev = 0;
@@ -1012,8 +1308,6 @@ extern "C" int dincae_adam_update_factored(float* w, float* m, float* v, int ldw
              reinterpret_cast<uint32_t*>(w8));
   else {
     // Bt <= 16: the TMA pipeline (DINCAE_ADAM_TMA=0 selects the register-staged kernel)
-    const char* e_tma = getenv("DINCAE_ADAM_TMA");       // read per call: the tests switch between the two
-    const bool use_tma = e_tma ? atoi(e_tma) != 0 : true;
     if (use_tma && Bt <= 16) {
       static int sm_count = 0;
       static bool attr_set = false;

@@ -200,3 +200,44 @@ def test_tma_pipelined_adam_equals_the_register_staged_kernel(rows, K, N, with_w
             check(lib.dincae_dense_tc_tile_weights(ptr(w), N, K, N, ptr(ref8), stream()))
             torch.cuda.synchronize()
             assert torch.equal(w8, ref8)
+
+
+@pytest.mark.parametrize("world,rows,K,N", [(2, 16, 536, 2648), (4, 16, 2648, 536), (8, 16, 1040, 776), (3, 7, 136, 72),
+                                            (1, 100, 520, 1032), (2, 9, 8296, 264)])
+def test_tma_pipelined_tensor_core_adam_equals_the_staged_kernels(world, rows, K, N, monkeypatch):
+    """adam_factored_tma_mma_kernel (16 < frames <= 128: TMA-swizzled p/m/v tiles, B fragments in
+    registers, column-block walk) against adam_factored_mma_kernel / _persist_kernel: the same
+    mma.sync sequence -> bit-identical m, v; weights within the approximate-division bound; bf16
+    tile copy consistent; ragged tiles, several tasks per CTA and fewer tasks than CTAs."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(world * 31 + rows)
+    stride_x, stride_z = rows * K + 32, rows * N + 64
+    x = torch.randn(world, stride_x, generator=g).to(torch.bfloat16).float().cuda()
+    dz = torch.randn(world, stride_z, generator=g).to(torch.bfloat16).float().cuda()
+    w0 = torch.randn(K, N, generator=g).cuda()
+    state = torch.tensor([0.9, 0.999, 0.0, 1e-2, 0.8, 0, 0, 0], dtype=torch.float32, device="cuda")
+    denom = torch.tensor([3.0], dtype=torch.float64, device="cuda")
+    out = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DINCAE_ADAM_TMA", mode)
+        w, m, v = w0.clone(), torch.zeros(K, N, device="cuda"), torch.zeros(K, N, device="cuda")
+        w8 = torch.zeros(K * N, dtype=torch.bfloat16, device="cuda")
+        for _ in range(2):
+            check(lib.dincae_adam_update_factored(ptr(w), ptr(m), ptr(v), N, ptr(x), stride_x, K, ptr(dz), stride_z, N,
+                                                  world, rows, K, N, 1.0, ptr(denom), 0.9, 0.999, 1e-8, ptr(state),
+                                                  ptr(w8), stream()))
+        torch.cuda.synchronize()
+        out.append((w, m, v, w8))
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert bool(((out[0][0] - out[1][0]).abs() <= 2.4e-7 * out[0][0].abs().clamp(min=1.0)).all())
+    assert not torch.equal(out[0][0], w0)
+    for w, _, _, w8 in out:
+        ref8 = torch.zeros_like(w8)
+        check(lib.dincae_dense_tc_tile_weights(ptr(w), N, K, N, ptr(ref8), stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(w8, ref8)
+    # and against the exact product
+    dw = torch.cat([x[r, :rows * K].view(rows, K) for r in range(world)]).double().t() @ \
+        torch.cat([dz[r, :rows * N].view(rows, N) for r in range(world)]).double()
+    gk = dw.float() * (0.8 / 3.0)
+    assert float((out[1][1] - (0.1 * gk + 0.9 * 0.1 * gk)).abs().max()) < 1e-4 * float(gk.abs().max())
