@@ -459,6 +459,10 @@ class Network:
         return self._conv_names[self.plan.L + l - 1]
 
     # ---- forward --------------------------------------------------------------------------
+    def params_changed(self):
+        """Call after writing ``self.params`` directly (restore, broadcast): refreshes copies
+        derived from the parameters.  Nothing to do for the fp32 / TF32 network."""
+
     def build_input(self, cube, frame_idx, cloud_idx, B, **kw):
         """Stack the network input of frames ``frame_idx[:B]`` from the device cube
         (``DeviceCube.build_batch``) into this network's input buffer."""
@@ -821,6 +825,11 @@ class NetworkBF16(Network):
 
     def set_params_tf(self, tf_params):
         super().set_params_tf(tf_params)
+        self.tile_dense_weights()
+
+    def params_changed(self):
+        """The tiled bf16 dense copies follow the fp32 master weights (the factored Adam kernels
+        keep them current during training; any other write to ``params`` must come through here)."""
         self.tile_dense_weights()
 
     def prepare_weights(self):

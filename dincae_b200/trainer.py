@@ -55,6 +55,7 @@ class Trainer:
         self.net.set_params_tf(tf_params if tf_params is not None else plan.glorot_init(init_seed))
         if self.dist is not None:
             self.dist.broadcast(self.net.params, src=0, group=self.group)
+            self.net.params_changed()
         self._nccl_in_graph = os.environ.get("DINCAE_NCCL_IN_GRAPH", "1") == "1"
         dev = cube.dev
         B = self.B
@@ -132,6 +133,7 @@ class Trainer:
         n = self.net
         for t, s in zip((n.params, n.adam_m, n.adam_v, n.adam_state), self._snap):
             t.copy_(s)
+        n.params_changed()          # the warm-up step also advanced the bf16 dense copies
         self._snap = None
 
     def set_lr(self, lr):

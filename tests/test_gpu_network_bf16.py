@@ -168,3 +168,36 @@ def test_bf16_step_is_deterministic_and_partial_batches_work():
     torch.cuda.synchronize()
     m_rec, s2 = M.head(M.forward(arch, params, xin))
     assert rel_err(net.m_rec[:B].cpu().numpy(), m_rec.numpy()) < 3e-2
+
+
+@pytest.mark.parametrize("factored", ["1", "0"])
+def test_graph_captured_bf16_trainer_equals_eager(factored, monkeypatch):
+    """The warm-up step run before graph capture is undone completely -- including the tiled bf16
+    copies of the dense kernels that the factored Adam kernel rewrites: losses and parameters of a
+    captured trainer equal the eager trainer's bit for bit from the first step on."""
+    import random
+    from dincae_b200.data import DeviceCube
+    from dincae_b200.sampler import TrainSampler
+    from dincae_b200.trainer import Trainer
+    from tests.util import random_cube
+    monkeypatch.setenv("DINCAE_FACTORED", factored)
+    rs = np.random.RandomState(21)
+    T, H, W, B = 12, 32, 32, 4
+    lon, lat, time_, fields = random_cube(rs, T, H, W, 2)
+    missing = [np.ma.getmaskarray(f) for f in fields]
+    cube = DeviceCube(lon, lat, time_, fields, missing, [1.0, 1.3], 3)
+    plan = Plan(H, W, cube.nvar, (16, 24, 40), (0.2,), (1, 2, 3), lanes=8)
+    runs = []
+    for use_graph in (False, True):
+        tr = Trainer(plan, cube, B, noise_seed=3, jitter_std=[0.05, 0.02], use_graph=use_graph, init_seed=4)
+        tr.set_lr(1e-3)
+        random.seed(5)
+        sm = TrainSampler(T, B, 4, seed=9)
+        for _ in range(3):
+            tr.train_step(*sm.next_batch())
+        runs.append((tr.flush_losses(), tr.net.params.clone(), [w.clone() for w in tr.net.w8]))
+        assert bool(tr.net.factored) == (factored == "1")
+    assert runs[0][0] == runs[1][0]
+    assert torch.equal(runs[0][1], runs[1][1])
+    for a, b in zip(runs[0][2], runs[1][2]):
+        assert torch.equal(a, b)

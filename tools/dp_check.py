@@ -1,5 +1,5 @@
 """Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py [A|D]
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py [A|D] [steps] [frames per rank]
 N ranks x B frames through Trainer(dist_group=True) must equal one rank with N*B frames after a few
 optimisation steps (same global index stream, same noise keys).  Every rank also runs the
 single-process reference itself, so no extra launch is needed.  Rank 0 prints one JSON line."""
@@ -30,6 +30,9 @@ if cfg == "A":
     T, H, W, B, filt, skip, lanes, nf = 120, 112, 112, 50, (16, 24, 36, 54), (1, 2, 3, 4), 4, 1
 else:
     T, H, W, B, filt, skip, lanes, nf = 40, 512, 512, 4, (32, 48, 72, 108, 162), (1, 2, 3, 4, 5), 8, 4
+if len(sys.argv) > 3:
+    B = int(sys.argv[3])                      # frames per rank (D with B > 8: the tensor-core Adam kernels)
+    T = max(T, 2 * B * 2 + 8)
 fields, missing = [], []
 for k, kind in enumerate(["sst", "chl", "wind", "wind"][:nf]):
     lon, lat, time_, data, mask = synthetic.sst_like_cube(T=T, H=H, W=W, seed=100 + k, kind=kind)
