@@ -51,6 +51,7 @@ struct WgBfParams {
   int R, TW, TWu, tiles_x, n_row_blocks, n_tiles;
   int M, N, slots, u_alloc, mt_count, tg_count, tpg, jobs, splits;
   int ones_mt, ones_slot;
+  int ones_sep, ones_off;      // bias row as a separate all-ones MMA (the planes fill the M tiles exactly); its 256 bytes
   int sbo_u, sbo_g, u_bytes, stage_bytes, n_stages;
   int tmem_cols;
   int tma_u0, tma_u1, tma_g;
@@ -134,7 +135,10 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
     for (int i = tid; i < n16; i += nthreads) reinterpret_cast<uint4*>(ring)[i] = u4_zero();
   }
   __syncthreads();
-  if (mt == P.ones_mt) {
+  if (P.ones_sep) {
+    // 256 bytes of bf16 ones behind the ring: operand A of the bias MMA (every M row, 16 pixels)
+    if (tid < 16) reinterpret_cast<uint4*>(ring + P.ones_off)[tid] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  } else if (mt == P.ones_mt) {
     // channel lane 0 of plane slot `ones_slot` = 1.0 (bf16 0x3f80) at every pixel of every stage
     const int npx = P.sbo_u >> 4;
     for (int s = 0; s < S; ++s) {
@@ -291,6 +295,11 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
 #pragma unroll
         for (int tl = 0; tl < 9; ++tl) ad[tl] = a_hi + (uint64_t)(u_lo + (uint32_t)P.toff[tap0 + tl]);
         uint64_t bd = b_hi + (uint64_t)g_lo;
+        // bias row as its own MMA (M rows of ones x G) when the planes leave no free slot in the M tile:
+        // SBO = 0, every plane slot of the operand aliases the same 256 bytes of ones
+        const bool bias_mma = P.ones_sep && mt == 0 && tg == 0;
+        const uint64_t od = ((uint64_t)(128u >> 4) << 16) | (1ull << 46) | (uint64_t)(smem_u32(ring + P.ones_off) >> 4);
+        const uint32_t bias_col = tmem_base + (uint32_t)(ntaps * P.N);
         const uint64_t a_skip = (uint64_t)(TWu - 16u * (uint32_t)ksteps), b_skip = (uint64_t)(TW - 16u * (uint32_t)ksteps);
         uint32_t accf = first_tile ? 0u : 1u;
         for (int r = 0; r < rows; ++r) {
@@ -298,6 +307,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
 #pragma unroll
             for (int tl = 0; tl < 9; ++tl)
               if (tl < ntaps) umma_f16(tmem_base + (uint32_t)(tl * P.N), ad[tl], bd, idesc, accf);
+            if (bias_mma) umma_f16(bias_col, od, bd, idesc, accf);
 #pragma unroll
             for (int tl = 0; tl < 9; ++tl) ad[tl] += 16u;
             bd += 16u;
@@ -330,7 +340,17 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
     float* out = P.partial + (size_t)split * (P.wsize + P.cout_pad);
     const int ci = 8 * plane0 + m;
     const bool row_w = m >= 0 && ci < 4 * P.cinp4 && ci < 8 * P.kp;
-    const bool row_b = mt == P.ones_mt && m == 8 * P.ones_slot;
+    const bool row_b = !P.ones_sep && mt == P.ones_mt && m == 8 * P.ones_slot;
+    if (P.ones_sep && mt == 0 && tg == 0 && warp == 0) {             // row 0 of the bias accumulator
+      for (int c0 = 0; c0 < P.N; c0 += 8) {
+        float a[8];
+        tmem_ld8(tmem_base + (uint32_t)(ntaps * P.N + c0), a);
+        if (lane == 0)
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (c0 + t < P.gp * 8 && c0 + t < P.cout_pad) out[P.wsize + c0 + t] = a[t];
+      }
+    }
     int chunk = 0;
     for (int tl = 0; tl < ntaps; ++tl) {
       const int tap = tap0 + tl;
@@ -367,25 +387,32 @@ static bool wgrad_bf16_plan(WgBfParams& P, int sm_count) {
   if (P.kp <= 0 || P.gp <= 0 || P.gp * 8 > 256) return false;
   if ((long long)P.B * (P.kp > P.gp ? P.kp : P.gp) * P.H * P.W >= (1ll << 31)) return false;
   // M-tiles: the real planes plus one slot for the constant-one channel
-  if (P.kp + 1 <= 8) {
+  // When the planes fill their tiles exactly (8 planes: the last decoder layer of configs[3], 32 + 28
+  // channels), the bias row would cost a whole extra tile (M = 128 instead of 64, or one more job):
+  // it becomes a separate MMA with an all-ones operand instead (23 clk per K step against
+  // 9 x 16 clk for the larger M).
+  if (P.kp <= 8) {
     P.M = 64;
     P.slots = 8;
   } else {
     P.M = 128;
     P.slots = 16;
   }
-  P.mt_count = (P.kp + 1 + P.slots - 1) / P.slots;
-  P.ones_mt = P.kp / P.slots;
-  P.ones_slot = P.kp % P.slots;
-  P.u_alloc = P.kp + 1 < P.slots ? P.kp + 1 : P.slots;
+  P.ones_sep = (P.kp % P.slots == 0) ? 1 : 0;
+  const int rows_needed = P.kp + (P.ones_sep ? 0 : 1);
+  P.mt_count = (rows_needed + P.slots - 1) / P.slots;
+  P.ones_mt = P.ones_sep ? 0 : P.kp / P.slots;
+  P.ones_slot = P.ones_sep ? -1 : P.kp % P.slots;
+  P.u_alloc = rows_needed < P.slots ? rows_needed : P.slots;
   P.N = P.M == 128 ? (P.gp * 8 + 15) / 16 * 16 : P.gp * 8;
   if (P.N < 16) P.N = 16;
   if (P.N > 256) return false;
-  const int tpg_max = 512 / P.N;
+  const int tpg_max = 512 / P.N - (P.ones_sep ? 1 : 0);
+  if (tpg_max < 1) return false;
   P.tg_count = (9 + tpg_max - 1) / tpg_max;
   P.tpg = (9 + P.tg_count - 1) / P.tg_count;
   P.jobs = P.mt_count * P.tg_count;
-  P.tmem_cols = wb_pow2_cols(P.tpg * P.N);
+  P.tmem_cols = wb_pow2_cols((P.tpg + (P.ones_sep ? 1 : 0)) * P.N);
   // column tiling: the width (multiple of 16, at most 112: the TMA box holds <= 256 elements of
   // 8 bytes per row) that stages the fewest pixels
   int best_tw = 0;
@@ -413,14 +440,14 @@ static bool wgrad_bf16_plan(WgBfParams& P, int sm_count) {
   int bestR = 0, bestS = 0;
   for (int S = 2; S >= 1 && !bestR; --S)
     for (int R = 1; R <= 16 && R <= P.H; ++R)
-      if (S * stage_bytes(R) + slack(R) + 128 <= WB_SMEM_BUDGET) {
+      if (S * stage_bytes(R) + slack(R) + 128 + 256 <= WB_SMEM_BUDGET) {
         bestR = R;
         bestS = S;
       }
   if (!bestR) return false;
   P.R = bestR;
   P.n_stages = bestS;
-  if (bestS == 2 && 3 * stage_bytes(bestR) + slack(bestR) + 128 <= WB_SMEM_BUDGET) P.n_stages = 3;
+  if (bestS == 2 && 3 * stage_bytes(bestR) + slack(bestR) + 128 + 256 <= WB_SMEM_BUDGET) P.n_stages = 3;
   P.sbo_u = (int)(((long long)(P.R + 2) * P.TWu * 16 + 127) / 128 * 128);
   P.sbo_g = P.R * P.TW * 16;
   for (int t = 0; t < 12; ++t) P.toff[t] = t < 9 ? (t / 3) * P.TWu + (t % 3) : 0;
@@ -430,6 +457,7 @@ static bool wgrad_bf16_plan(WgBfParams& P, int sm_count) {
   P.b_hi = ((unsigned long long)(128u >> 4) << 16) | ((unsigned long long)((unsigned)P.sbo_g >> 4) << 32) | (1ull << 46);
   P.u_bytes = P.u_alloc * P.sbo_u;
   P.stage_bytes = (int)stage_bytes(P.R);
+  P.ones_off = (int)(((long long)P.n_stages * P.stage_bytes + slack(P.R) + 127) / 128 * 128);
   P.n_row_blocks = (P.H + P.R - 1) / P.R;
   const long long nt = (long long)P.B * P.n_row_blocks * P.tiles_x;
   if (nt > (1ll << 30)) return false;
@@ -531,7 +559,7 @@ extern "C" int dincae_conv3x3_wgrad_bf16(const void* src0, int c0p, int src0_hal
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)P.n_stages * P.stage_bytes + (size_t)(P.slots - P.u_alloc) * P.sbo_u + 128;
+  const size_t smem = (size_t)P.ones_off + 256 + 128;
   {
     static int lw = 0, pa = -1;
     if (pa < 0) {

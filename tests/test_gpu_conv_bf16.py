@@ -74,7 +74,9 @@ def pack_weights(lib, k, splits, cout_pad, nd, ci_first=0):
 
 ENC_CASES = [(2, 12, 20, 10, 16), (3, 15, 11, 16, 24), (2, 7, 7, 36, 54), (1, 112, 112, 10, 16),
              (2, 33, 70, 5, 3), (1, 20, 24, 72, 108), (1, 18, 16, 108, 162),
-             (1, 20, 200, 28, 32), (2, 9, 131, 5, 3), (1, 40, 136, 32, 48)]
+             (1, 20, 200, 28, 32), (2, 9, 131, 5, 3), (1, 40, 136, 32, 48),
+             # input planes fill the weight-gradient M tile exactly: bias row as its own all-ones MMA
+             (1, 16, 24, 64, 40), (1, 12, 16, 128, 24)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", ENC_CASES)
