@@ -289,7 +289,7 @@ conv3x3_wgrad_bf16_kernel(const WgBfParams P, const __grid_constant__ CUtensorMa
         // 64-bit descriptor per tap and advances it by 16 pixels per K step, so that no MMA waits
         // on an address computation: a dependent chain of uniform-datapath instructions per MMA
         // (indexed constant load -> add -> mask -> add) cost ~70 clk per MMA in the first version
-        // (role timeline, profiles/r2_summary.md).  Start addresses stay below 2^14 16-byte units
+        // (role timeline of DINCAE_WB_DEBUG=1).  Start addresses stay below 2^14 16-byte units
         // (228 KB of shared memory), so the descriptor's address field never overflows.
         uint64_t ad[9];
 #pragma unroll

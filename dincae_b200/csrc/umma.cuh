@@ -30,7 +30,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Wait for a phase of an mbarrier: every lane of the (converged) warp polls.  Measured against
-// a lane-0-only poll + __syncwarp (profiles/r2_summary.md): the single-lane variant takes the
+// a lane-0-only poll + __syncwarp (A/B bench runs of round 2): the single-lane variant takes the
 // polling traffic off the shared-memory pipe but wakes the warp up later, and the config-A step
 // (many short kernels) was 6.7 % slower with it (0.736 vs 0.690 ms); the bf16 kernels at 512x512
 // did not change.  So: all lanes poll.
