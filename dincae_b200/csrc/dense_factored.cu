@@ -286,7 +286,8 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int AM_XP = 20;      // padded row lengths of the staged factors (bank-conflict free fragments)
+constexpr int AM_XP = 24;      // padded row lengths of the staged factors: frames t = 0..3 of a fragment start 24 floats
+                               // apart = banks 0, 24, 16, 8 (20 put t = 3 on banks 28..35, a 2-way conflict with t = 0: ncu)
 constexpr int AM_ZP = 264;
 
 __global__ void __launch_bounds__(256, 2) adam_factored_mma_kernel(float* __restrict__ w, float* __restrict__ m,
@@ -767,7 +768,7 @@ static int at_encode_map(CUtensorMap* tm, const float* base, int K, int N, int l
 //   * a 17th warp issues the 48 tensor-map loads / stores per tile (the compute warps hand a
 //     finished stage over through an mbarrier), w8 staging is per stage.
 // ---------------------------------------------------------------------------------------------
-constexpr int AX_XP = 20;                                 // padded frame pitch of the x chunk (floats)
+constexpr int AX_XP = 24;                                 // padded frame pitch of the x chunk (floats; see AM_XP)
 constexpr int AX_CWARPS = 16;
 constexpr int AX_THREADS = 32 * AX_CWARPS + 32;
 constexpr int AX_OFF_W8 = AT_STAGES * 3 * AT_TILE * 4;     // 3 x 8 KB bf16 staging (one per stage)
