@@ -869,7 +869,9 @@ __global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
 
   // ---------------- compute warps ------------------------------------------------------------------
   const int g = lane >> 2, t = lane & 3;
-  const int cw = 16 * warp;                                   // this warp's first column in the tile
+  // columns of this warp's two n-tiles: a warp pair shares a 32-column box, the even warp takes box
+  // columns 0-7 and 16-23, the odd warp 8-15 and 24-31 (n-tile j at cw + 16 j) -- see toff below
+  const int cw = 32 * (warp >> 1) + 8 * (warp & 1);
   float gscale = grad_scale;
   if (denom) gscale /= (float)(*denom);
   const float gs = gscale * state[4];
@@ -894,14 +896,21 @@ __global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
   named_bar_sync(1, 32 * AX_CWARPS);
   uint32_t bfr[NK][2][2];
   int cur_task = -1;
-  // swizzled position of this thread's float2 in a 16 x 256 tile (eight 16 x 32 boxes of 2 KB,
-  // 128-byte rows, 16-byte chunk index ^= row % 8): rows g and g + 8, n-tiles j = 0, 1
+  // Swizzled position of this thread's float2 in a 16 x 256 tile (eight 16 x 32 boxes of 2 KB,
+  // 128-byte rows, 16-byte chunk index ^= row % 8), rows g and g + 8.  In pass q the lanes with
+  // t < 2 work on n-tile q and the lanes with t >= 2 on n-tile q ^ 1: the two halves of a half
+  // warp then touch chunks of different 4-chunk groups (the n-tiles are 16 columns apart), the
+  // row phases g = 0..3 spread each over its group, and the 64-bit accesses are conflict free.
+  // (Both halves on the same n-tile hit adjacent chunks c, c + 1, which the same four phases map
+  // onto the same four positions: 2-way conflicts on every access, profiles/r2_adam_ncu.md.)
   int toff[2];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int chunk = 4 * (warp & 1) + 2 * j + (t >> 1);
-    toff[j] = (warp >> 1) * 2048 + g * 128 + ((chunk ^ g) << 4) + (t & 1) * 8;
+  for (int q = 0; q < 2; ++q) {
+    const int j = q ^ (t >> 1);
+    const int chunk = 2 * (warp & 1) + 4 * j + (t >> 1);
+    toff[q] = (warp >> 1) * 2048 + g * 128 + ((chunk ^ g) << 4) + (t & 1) * 8;
   }
+  const bool hi_half = (t >> 1) != 0;
   for (int i = 0; it.valid(); ++i) {
     const int s = i % AT_STAGES;
     if (it.task != cur_task) {                                // B fragments: dz of the warp's columns, all frames
@@ -912,7 +921,7 @@ __global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int f = 8 * ks + t + 4 * h, col = n0 + cw + 8 * j + g;
+            const int f = 8 * ks + t + 4 * h, col = n0 + cw + 16 * j + g;
             const bool ok = f < Bt && col < N;
             bfr[ks][j][h] = ok ? __float_as_uint(__ldg(factor_row(fz, f, rows_per_rank) + col)) : 0u;
           }
@@ -942,15 +951,16 @@ __global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int at = toff[j] + r * 1024;                    // row g + 8 r: same swizzle phase
+      for (int q = 0; q < 2; ++q) {
+        const int j = q ^ (hi_half ? 1 : 0);                  // this lane's n-tile in pass q
+        const int at = toff[q] + r * 1024;                    // row g + 8 r: same swizzle phase
         const float2 p2 = *reinterpret_cast<const float2*>(tw + at);
         const float2 m2 = *reinterpret_cast<const float2*>(tw + AT_TILE * 4 + at);
         const float2 v2 = *reinterpret_cast<const float2*>(tw + 2 * AT_TILE * 4 + at);
         float pa[2] = {p2.x, p2.y}, ma[2] = {m2.x, m2.y}, va[2] = {v2.x, v2.y};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const float gk = acc[j][2 * r + c] * gs;
+          const float gk = ((q == 0) != hi_half ? acc[0][2 * r + c] : acc[1][2 * r + c]) * gs;
           ma[c] = ma[c] + (gk - ma[c]) * omb1;
           va[c] = va[c] + (gk * gk - va[c]) * omb2;
           pa[c] = pa[c] - __fdividef(ma[c] * lr_t, sqrt_approx(va[c]) + eps);
@@ -958,7 +968,7 @@ __global__ void __launch_bounds__(AX_THREADS, 1) adam_factored_tma_mma_kernel(
         *reinterpret_cast<float2*>(tw + at) = make_float2(pa[0], pa[1]);
         *reinterpret_cast<float2*>(tw + AT_TILE * 4 + at) = make_float2(ma[0], ma[1]);
         *reinterpret_cast<float2*>(tw + 2 * AT_TILE * 4 + at) = make_float2(va[0], va[1]);
-        const int row = g + 8 * r, col = cw + 8 * j + 2 * t;
+        const int row = g + 8 * r, col = cw + 16 * j + 2 * t;
         if (w8) wst[((row >> 3) * 32 + (col >> 3)) * 32 + (row & 7) * 4 + ((col & 7) >> 1)] = bf2_pack(pa[0], pa[1]);
       }
     asm volatile("cp.async.wait_all;" ::: "memory");          // next x chunk
