@@ -427,7 +427,10 @@ def e2e_api_leg(a, world, rank, dist, barrier, K):
     # The reference trains epochs=1000 by default (DINCAE/__init__.py:307); 100 keeps the bench
     # short.  Every one-off cost of the call (netCDF read, upload, kernel / graph set-up, the final
     # reconstruction and its file) is inside the timed region and is amortised over these epochs.
-    E = a.e2e_epochs if a.e2e_epochs > 0 else max(1, ceil(K / spe))
+    # Weak scaling like the device-timed leg: the epoch count grows with the number of ranks, so every
+    # rank runs (about) the same number of optimisation steps at every N and the one-off costs are
+    # amortised over the same per-rank work.
+    E = a.e2e_epochs * world if a.e2e_epochs > 0 else max(1, ceil(K / spe))
     loss = []
     barrier()
     t0 = time.perf_counter()
@@ -453,7 +456,9 @@ def e2e_api_leg(a, world, rank, dist, barrier, K):
            "note": "timed region = DINCAE.reconstruct_gridded_nc(file, 'SST', outdir, epochs=%d, batch_size=%d, "
                    "save_each=0): netCDF read of the %d-frame cube, upload, %d optimisation steps "
                    "(loss.append each), reconstruction of all %d frames and the output netCDF file; "
-                   "value = trained frames / wall seconds of the whole call" % (E, a.batch, a.ntime, steps, a.ntime)}
+                   "value = trained frames / wall seconds of the whole call; epochs = %d x n_gpus (weak "
+                   "scaling: the same number of steps per rank at every N)" % (E, a.batch, a.ntime, steps, a.ntime,
+                                                                              a.e2e_epochs)}
     if rank == 0:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
